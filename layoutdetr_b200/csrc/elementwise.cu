@@ -1,0 +1,304 @@
+// Bytes-bound elementwise kernels: bias_act (StyleGAN2 fused bias + activation + gain + clamp with
+// first/second-order gradient modes), fma, dtype casts with row padding, broadcast add, activation
+// backward for GEMM-fused activations, per-sample channel modulation.  All are grid-stride with
+// 128-bit vector accesses where alignment allows; grids are sized in multiples of the SM count.
+#include "common.cuh"
+#include "runtime.h"
+#include <algorithm>
+
+namespace {
+using namespace ld;
+
+inline int ew_grid(long n_items, int threads) {
+    const long blocks = (n_items + threads - 1) / threads;
+    const long cap = (long)sm_count() * 8;
+    return (int)std::max<long>(1, std::min(blocks, cap));
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p, long i);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, long i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p, long i) { return bf16_to_f32(p[i]); }
+template <typename T> __device__ __forceinline__ void stf(T* p, long i, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, long i, float v) { p[i] = v; }
+template <> __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, long i, float v) { p[i] = f32_to_bf16(v); }
+
+// ---------------------------------------------------------------------------------------------
+// bias_act.  Semantics follow torch_utils/ops/bias_act.py:92-125 (_bias_act_ref) for the forward
+// and torch_utils/ops/bias_act.cu:24-148 for the gradient modes:
+//   grad = 0: y = clamp(act(x + b) * gain)
+//   grad = 1: x is dy; returns d/dx of the forward, evaluated from xref (+b) / yref
+//   grad = 2: x is d_dx; returns the second-order term (dy supplied), for act with has_2nd_grad
+// Activation ids are the reference's cuda_idx (1 linear .. 9 swish).
+// ---------------------------------------------------------------------------------------------
+struct BiasActArgs {
+    const void* x; const void* b; const void* xref; const void* yref; const void* dy; void* y;
+    int grad, act; float alpha, gain, clamp;
+    long sizeX; int sizeB; long stepB;
+};
+
+template <int A>
+__device__ __forceinline__ float bias_act_eval(int G, float x, float xref, float yy, float alpha, float& yref, float gain) {
+    const float expRange = 80.f, halfExpRange = 40.f;
+    const float seluScale = 1.0507009873554804934193349852946f, seluAlpha = 1.6732632423543772848170429916717f;
+    float y = 0.f;
+    if (A == 1) { if (G <= 1) y = x; }
+    else if (A == 2) { y = (G == 0) ? fmaxf(x, 0.f) : (G == 1 ? (yy > 0.f ? x : 0.f) : 0.f); }
+    else if (A == 3) { y = (G == 0) ? (x > 0.f ? x : x * alpha) : (G == 1 ? (yy > 0.f ? x : x * alpha) : 0.f); }
+    else if (A == 4) {
+        if (G == 0) { const float c = expf(x), d = 1.f / c; y = (x < -expRange) ? -1.f : (x > expRange) ? 1.f : (c - d) / (c + d); }
+        else if (G == 1) y = x * (1.f - yy * yy);
+        else y = x * (1.f - yy * yy) * (-2.f * yy);
+    } else if (A == 5) {
+        if (G == 0) y = (x < -expRange) ? 0.f : 1.f / (expf(-x) + 1.f);
+        else if (G == 1) y = x * yy * (1.f - yy);
+        else y = x * yy * (1.f - yy) * (1.f - 2.f * yy);
+    } else if (A == 6) {
+        if (G == 0) y = (x >= 0.f) ? x : expf(x) - 1.f;
+        else if (G == 1) y = (yy >= 0.f) ? x : x * (yy + 1.f);
+        else y = (yy >= 0.f) ? 0.f : x * (yy + 1.f);
+    } else if (A == 7) {
+        if (G == 0) y = (x >= 0.f) ? seluScale * x : (seluScale * seluAlpha) * (expf(x) - 1.f);
+        else if (G == 1) y = (yy >= 0.f) ? x * seluScale : x * (yy + seluScale * seluAlpha);
+        else y = (yy >= 0.f) ? 0.f : x * (yy + seluScale * seluAlpha);
+    } else if (A == 8) {
+        if (G == 0) y = (x > expRange) ? x : logf(expf(x) + 1.f);
+        else if (G == 1) y = x * (1.f - expf(-yy));
+        else { const float c = expf(-yy); y = x * c * (1.f - c); }
+    } else if (A == 9) {
+        if (G == 0) y = (x < -expRange) ? 0.f : x / (expf(-x) + 1.f);
+        else {
+            const float c = expf(xref), d = c + 1.f;
+            if (G == 1) y = (xref > halfExpRange) ? x : x * c * (xref + d) / (d * d);
+            else y = (xref > halfExpRange) ? 0.f : x * c * (xref * (2.f - d) + 2.f * d) / (d * d * d);
+            yref = (xref < -expRange) ? 0.f : xref / (expf(-xref) + 1.f) * gain;
+        }
+    }
+    return y;
+}
+
+template <typename T, int A>
+__global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
+    const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = (const T*)p.xref;
+    const T* yr = (const T*)p.yref; const T* dyp = (const T*)p.dy; T* y = (T*)p.y;
+    const int G = p.grad;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.sizeX; i += (long)gridDim.x * blockDim.x) {
+        float xv = ldf<T>(x, i);
+        const float bv = b ? ldf<T>(b, (i / p.stepB) % p.sizeB) : 0.f;
+        float xref = xr ? ldf<T>(xr, i) : 0.f;
+        float yref = yr ? ldf<T>(yr, i) : 0.f;
+        const float dy = dyp ? ldf<T>(dyp, i) : 1.f;
+        const float yy = (p.gain != 0.f) ? yref / p.gain : 0.f;
+        if (G == 0) xv += bv; else xref += bv;
+        float out = bias_act_eval<A>(G, xv, xref, yy, p.alpha, yref, p.gain);
+        out *= p.gain * dy;
+        if (p.clamp >= 0.f) {
+            if (G == 0) out = (out > -p.clamp && out < p.clamp) ? out : (out >= 0.f ? p.clamp : -p.clamp);
+            else out = (yref > -p.clamp && yref < p.clamp) ? out : 0.f;
+        }
+        stf<T>(y, i, out);
+    }
+}
+
+template <typename T>
+int launch_bias_act(const BiasActArgs& p, cudaStream_t st) {
+    const int grid = ew_grid(p.sizeX, 256);
+    switch (p.act) {
+        case 1: bias_act_kernel<T, 1><<<grid, 256, 0, st>>>(p); break;
+        case 2: bias_act_kernel<T, 2><<<grid, 256, 0, st>>>(p); break;
+        case 3: bias_act_kernel<T, 3><<<grid, 256, 0, st>>>(p); break;
+        case 4: bias_act_kernel<T, 4><<<grid, 256, 0, st>>>(p); break;
+        case 5: bias_act_kernel<T, 5><<<grid, 256, 0, st>>>(p); break;
+        case 6: bias_act_kernel<T, 6><<<grid, 256, 0, st>>>(p); break;
+        case 7: bias_act_kernel<T, 7><<<grid, 256, 0, st>>>(p); break;
+        case 8: bias_act_kernel<T, 8><<<grid, 256, 0, st>>>(p); break;
+        case 9: bias_act_kernel<T, 9><<<grid, 256, 0, st>>>(p); break;
+        default: set_last_error("bias_act: unknown activation id %d", p.act); return LD_ERR_INVALID_ARG;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic helpers
+// ---------------------------------------------------------------------------------------------
+// dst[r, 0:cols_dst] = (c < cols_src) ? src[r, c] : 0   with dtype conversion
+template <typename TS, typename TD>
+__global__ void cast_pad_kernel(const TS* __restrict__ src, long lds, TD* __restrict__ dst, long ldd, long rows, int cols_src, int cols_dst) {
+    const long total = rows * (long)cols_dst;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / cols_dst; const int c = (int)(i - r * cols_dst);
+        stf<TD>(dst, r * ldd + c, c < cols_src ? ldf<TS>(src, r * lds + c) : 0.f);
+    }
+}
+
+// contiguous vectorised cast (n % 4 == 0, 16-byte aligned)
+__global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long n4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 a = src[i];
+        uint2 o; o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+        dst[i] = o;
+    }
+}
+
+// out[i] = a[i] * alpha + b[i % period] * beta
+template <typename TA, typename TB, typename TO>
+__global__ void axpby_bcast_kernel(const TA* __restrict__ a, const TB* __restrict__ b, TO* __restrict__ out, long n, long period, float alpha, float beta) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        stf<TO>(out, i, ldf<TA>(a, i) * alpha + ldf<TB>(b, i % period) * beta);
+}
+
+// dx = dy * act'(.)  for activations fused into the GEMM epilogue.
+//   relu / lrelu / sigmoid use the activation OUTPUT y (ref = y); gelu uses the PRE-activation (ref = x).
+template <typename TG, typename TR, typename TO>
+__global__ void act_bwd_kernel(const TG* __restrict__ dy, const TR* __restrict__ ref, TO* __restrict__ dx, long n, int act, float gain) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float g = ldf<TG>(dy, i) * gain; const float r = ldf<TR>(ref, i);
+        float d;
+        switch (act) {
+            case LD_ACT_RELU:    d = r > 0.f ? g : 0.f; break;
+            case LD_ACT_LRELU:   d = r > 0.f ? g : 0.2f * g; break;
+            case LD_ACT_GELU:    d = g * gelu_erf_grad(r); break;
+            case LD_ACT_SIGMOID: { const float y = r / gain; d = g * y * (1.f - y); } break;
+            default:             d = g; break;
+        }
+        stf<TO>(dx, i, d);
+    }
+}
+
+// column sums of a [rows, cols] matrix accumulated into out[cols] (bias gradients)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long ld, float* __restrict__ out, long rows, int cols, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long r0 = (long)blockIdx.y * rows_per_block;
+    const long r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+    for (long r = r0; r < r1; ++r) s += ldf<T>(x, r * ld + c);
+    atomicAdd(out + c, s);
+}
+
+// y[b, i, c] = x[b, i, c] * s[b, c]   (channels-last per-sample modulation; inner = C)
+template <typename TX, typename TO>
+__global__ void scale_channels_kernel(const TX* __restrict__ x, const float* __restrict__ s, TO* __restrict__ y, long n, long per_sample, int C) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / per_sample; const int c = (int)(i % C);
+        stf<TO>(y, i, ldf<TX>(x, i) * s[b * C + c]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Mirrors bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:33-97): caller-owned output.
+int ld_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                int dtype, int grad, int act, float alpha, float gain, float clamp,
+                int64_t sizeX, int sizeB, int64_t stepB, void* stream) {
+    LD_CHECK_ARG(x && y && sizeX > 0, "bias_act: null tensor or empty size");
+    LD_CHECK_ARG(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2");
+    LD_CHECK_ARG(b == nullptr || (sizeB > 0 && stepB > 0), "bias_act: bias given but sizeB/stepB invalid");
+    LD_CHECK_ARG(dtype == LD_F32 || dtype == LD_BF16, "bias_act: dtype must be f32 or bf16");
+    BiasActArgs p{x, b, xref, yref, dy, y, grad, act, alpha, gain, clamp, (long)sizeX, sizeB > 0 ? sizeB : 1, stepB > 0 ? (long)stepB : 1};
+    int e = (dtype == LD_F32) ? launch_bias_act<float>(p, (cudaStream_t)stream) : launch_bias_act<__nv_bfloat16>(p, (cudaStream_t)stream);
+    if (e) return e;
+    ld::count_launch();
+    LD_LAUNCH_CHECK("bias_act");
+    return 0;
+}
+
+// fma(a, b, c) = a * b + c with b, c broadcast per (sample, channel) or full-size
+// (torch_utils/ops/fma.py:16; used by modulated_conv2d's demodulate+noise branch, networks_stylegan2.py:70)
+__global__ void fma_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ y,
+                           long n, long b_period, long b_div, long c_period, long c_div) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = fmaf(a[i], b[(i / b_div) % b_period], c[(i / c_div) % c_period]);
+}
+int ld_fma_f32(const float* a, const float* b, const float* c, float* y, int64_t n,
+               int64_t b_period, int64_t b_div, int64_t c_period, int64_t c_div, void* stream) {
+    LD_CHECK_ARG(a && b && c && y && n > 0 && b_period > 0 && b_div > 0 && c_period > 0 && c_div > 0, "fma: bad argument");
+    fma_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, y, n, b_period, b_div, c_period, c_div);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("fma");
+    return 0;
+}
+
+int ld_cast_pad(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+                int64_t rows, int cols_src, int cols_dst, void* stream) {
+    LD_CHECK_ARG(src && dst && rows > 0 && cols_src > 0 && cols_dst >= cols_src, "cast_pad: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long total = rows * (long)cols_dst;
+    if (src_dtype == LD_F32 && dst_dtype == LD_BF16 && cols_src == cols_dst && lds == cols_src && ldd == cols_dst &&
+        total % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
+        cast_f32_bf16_vec_kernel<<<ew_grid(total / 4, 256), 256, 0, st>>>((const float4*)src, (uint2*)dst, total / 4);
+    } else {
+        const int grid = ew_grid(total, 256);
+#define CP(TS, TD) cast_pad_kernel<TS, TD><<<grid, 256, 0, st>>>((const TS*)src, lds, (TD*)dst, ldd, rows, cols_src, cols_dst)
+        if (src_dtype == LD_F32 && dst_dtype == LD_BF16) CP(float, __nv_bfloat16);
+        else if (src_dtype == LD_BF16 && dst_dtype == LD_F32) CP(__nv_bfloat16, float);
+        else if (src_dtype == LD_F32) CP(float, float);
+        else CP(__nv_bfloat16, __nv_bfloat16);
+#undef CP
+    }
+    ld::count_launch();
+    LD_LAUNCH_CHECK("cast_pad");
+    return 0;
+}
+
+int ld_axpby_bcast(const void* a, int a_dtype, const void* b, int b_dtype, void* out, int out_dtype,
+                   int64_t n, int64_t period, float alpha, float beta, void* stream) {
+    LD_CHECK_ARG(a && b && out && n > 0 && period > 0, "axpby_bcast: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ew_grid(n, 256);
+#define AX(TA, TB, TO) axpby_bcast_kernel<TA, TB, TO><<<grid, 256, 0, st>>>((const TA*)a, (const TB*)b, (TO*)out, n, period, alpha, beta)
+    const int key = a_dtype * 4 + b_dtype * 2 + out_dtype;
+    switch (key) {
+        case 0: AX(float, float, float); break;
+        case 1: AX(float, float, __nv_bfloat16); break;
+        case 2: AX(float, __nv_bfloat16, float); break;
+        case 3: AX(float, __nv_bfloat16, __nv_bfloat16); break;
+        case 4: AX(__nv_bfloat16, float, float); break;
+        case 5: AX(__nv_bfloat16, float, __nv_bfloat16); break;
+        case 6: AX(__nv_bfloat16, __nv_bfloat16, float); break;
+        default: AX(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+    }
+#undef AX
+    ld::count_launch();
+    LD_LAUNCH_CHECK("axpby_bcast");
+    return 0;
+}
+
+int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, void* dx, int dx_dtype,
+               int64_t n, int act, float gain, void* stream) {
+    LD_CHECK_ARG(dy && ref && dx && n > 0, "act_bwd: bad argument");
+    LD_CHECK_ARG(dy_dtype == LD_BF16 && ref_dtype == LD_BF16 && dx_dtype == LD_BF16, "act_bwd: bf16 only");
+    act_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ref, (__nv_bfloat16*)dx, n, act, gain);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("act_bwd");
+    return 0;
+}
+
+int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t rows, int cols, void* stream) {
+    LD_CHECK_ARG(x && out && rows > 0 && cols > 0, "colsum: bad argument");
+    const int rpb = (int)std::max<long>(32, (rows + 255) / 256);
+    dim3 grid(ld::ceil_div(cols, 128), ld::ceil_div(rows, rpb));
+    if (dtype == LD_F32) colsum_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)x, ld_, out, rows, cols, rpb);
+    else colsum_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld_, out, rows, cols, rpb);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("colsum");
+    return 0;
+}
+
+int ld_scale_channels(const void* x, int x_dtype, const float* s, void* y, int y_dtype, int64_t n, int64_t per_sample, int C, void* stream) {
+    LD_CHECK_ARG(x && s && y && n > 0 && per_sample > 0 && C > 0 && per_sample % C == 0, "scale_channels: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = ew_grid(n, 256);
+    if (x_dtype == LD_BF16 && y_dtype == LD_BF16) scale_channels_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, s, (__nv_bfloat16*)y, n, per_sample, C);
+    else if (x_dtype == LD_F32 && y_dtype == LD_BF16) scale_channels_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)y, n, per_sample, C);
+    else if (x_dtype == LD_BF16 && y_dtype == LD_F32) scale_channels_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, s, (float*)y, n, per_sample, C);
+    else scale_channels_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, s, (float*)y, n, per_sample, C);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("scale_channels");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+// Batched bf16 GEMM for sm_100a: TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (cta_group::1,
+// 128 x {128,256} x 16 UMMA, fp32 accumulators double-buffered in TMEM) -> fused epilogue.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).  The accumulator of tile i+1 is
+// produced while the epilogue drains tile i.
+//
+// Operand "major" flags let one kernel serve forward (A K-major, B K-major), dgrad (B MN-major) and
+// wgrad (A and B MN-major) without materialising transposes; two batch dims with arbitrary strides
+// let attention run straight on the fused [B*T, 3*H*d] QKV buffer.
+#include "common.cuh"
+#include "runtime.h"
+#include "../../include/layoutdetr_sm100.h"
+
+namespace {
+
+using namespace ld;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_STAGE_BYTES_MAX = 256 * BK * 2;     // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES_MAX;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;                     // TMEM columns per accumulator stage
+
+struct KParams {
+    int M, N, K, nb1, nb2;
+    int act, accumulate, split_k, d_dtype, r_dtype, bn;
+    int a_mn, b_mn;
+    int m_tiles, n_tiles, kb_total, kb_per_split, total_tiles;
+    int vec_ok;
+    float alpha, post_gain;
+    void* D; long ldd, d_sb1, d_sb2;
+    void* aux;
+    const void* R; long ldr, r_sb1, r_sb2;
+    const float* cs; const float* cb; long col_sb1, col_sb2;
+};
+
+struct Tile {
+    int b1, b2, m0, n0, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
+    Tile tl;
+    const int ks = t % p.split_k; t /= p.split_k;
+    const int nt = t % p.n_tiles; t /= p.n_tiles;
+    const int mt = t % p.m_tiles; t /= p.m_tiles;
+    tl.b2 = t % p.nb2;
+    tl.b1 = t / p.nb2;
+    tl.m0 = mt * BM;
+    tl.n0 = nt * p.bn;
+    tl.kb_begin = ks * p.kb_per_split;
+    tl.kb_end = min(p.kb_total, tl.kb_begin + p.kb_per_split);
+    return tl;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case LD_ACT_RELU:    return fmaxf(v, 0.0f);
+        case LD_ACT_GELU:    return gelu_erf(v);
+        case LD_ACT_LRELU:   return v > 0.0f ? v : 0.2f * v;
+        case LD_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+        default:             return v;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar  = full_bar + STAGES;
+    uint64_t* tfull_bar  = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot  = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = A_STAGE_BYTES + p.bn * BK * 2;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const Tile tl = decode_tile(p, t);
+                for (int kb = tl.kb_begin; kb < tl.kb_end; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    const int k0 = kb * BK;
+                    if (!p.a_mn) {
+                        tma_load_4d(sa, &tmA, &full_bar[stage], k0, tl.m0, tl.b2, tl.b1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], tl.m0 + 64 * j, k0, tl.b2, tl.b1);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_4d(sb, &tmB, &full_bar[stage], k0, tl.n0, tl.b2, tl.b1);
+                    } else {
+                        for (int j = 0; j < p.bn / 64; ++j)
+                            tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], tl.n0 + 64 * j, k0, tl.b2, tl.b1);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            const uint32_t idesc = make_idesc_bf16(BM, p.bn, p.a_mn, p.b_mn);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const Tile tl = decode_tile(p, t);
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+                for (int kb = tl.kb_begin; kb < tl.kb_end; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major: 32 B per UMMA_K step inside the 128 B swizzle row; 8-row groups 1024 B apart.
+                        // MN-major: 16 K-rows (2 x 1024 B) per step; 64-wide MN blocks 8192 B apart.
+                        const uint64_t da = p.a_mn ? make_smem_desc(sa + k * 2048, 8192, 1024)
+                                                   : make_smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024)
+                                                   : make_smem_desc(sb + k * 32, 16, 1024);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (kb > tl.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+                as ^= 1; if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;                       // TMEM lane quadrant of this warp
+        int as = 0; uint32_t aphase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const Tile tl = decode_tile(p, t);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int row = tl.m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const long d_off = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2 + (long)row * p.ldd;
+            const long r_off = (long)tl.b1 * p.r_sb1 + (long)tl.b2 * p.r_sb2 + (long)row * p.ldr;
+            const long c_off = (long)tl.b1 * p.col_sb1 + (long)tl.b2 * p.col_sb2;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
+            for (int c0 = 0; c0 < p.bn; c0 += 16) {
+                const int n_base = tl.n0 + c0;
+                if (n_base >= p.N) break;             // warp-uniform
+                uint32_t r[16];
+                tmem_ld_x16(taddr + c0, r);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                const bool full_chunk = (n_base + 16 <= p.N);
+                if (p.cs) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] *= __ldg(p.cs + c_off + n_base + i);
+                }
+                if (p.cb) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += __ldg(p.cb + c_off + n_base + i);
+                }
+                const bool vec = p.vec_ok && full_chunk;
+                if (p.R) {
+                    if (p.r_dtype == LD_BF16) {
+                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base;
+                        if (vec) {
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
+                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { float lo, hi; unpack_bf16x2(w[i], lo, hi); v[2 * i] += lo; v[2 * i + 1] += hi; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += bf16_to_f32(rp[i]);
+                        }
+                    } else {
+                        const float* rp = reinterpret_cast<const float*>(p.R) + r_off + n_base;
+                        if (vec) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                                v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += rp[i];
+                        }
+                    }
+                }
+                if (p.aux) {
+                    if (p.d_dtype == LD_BF16) {
+                        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + d_off + n_base;
+                        if (vec) {
+                            uint4 a, b;
+                            a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+                            b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+                            reinterpret_cast<uint4*>(ap)[0] = a; reinterpret_cast<uint4*>(ap)[1] = b;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) ap[i] = f32_to_bf16(v[i]);
+                        }
+                    } else {
+                        float* ap = reinterpret_cast<float*>(p.aux) + d_off + n_base;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) ap[i] = v[i];
+                    }
+                }
+                if (p.act != LD_ACT_NONE) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
+                }
+                if (p.post_gain != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= p.post_gain;
+                }
+                if (p.d_dtype == LD_BF16) {
+                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n_base;
+                    if (p.accumulate == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += bf16_to_f32(dp[i]);
+                    }
+                    if (vec) {
+                        uint4 a, b;
+                        a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+                        b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+                        reinterpret_cast<uint4*>(dp)[0] = a; reinterpret_cast<uint4*>(dp)[1] = b;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = f32_to_bf16(v[i]);
+                    }
+                } else {
+                    float* dp = reinterpret_cast<float*>(p.D) + d_off + n_base;
+                    if (p.accumulate == 2) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) atomicAdd(dp + i, v[i]);
+                    } else {
+                        if (p.accumulate == 1) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += dp[i];
+                        }
+                        if (vec) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<float4*>(dp)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = v[i];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K, int nb1, int nb2, int box_rows) {
+    if (!op.ptr) { set_last_error("gemm: null operand"); return LD_ERR_INVALID_ARG; }
+    if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) != 0) { set_last_error("gemm: operand pointer %p not 16-byte aligned", op.ptr); return LD_ERR_ALIGNMENT; }
+    if (op.ld % 8 != 0 || (nb2 > 1 && op.sb2 % 8 != 0) || (nb1 > 1 && op.sb1 % 8 != 0)) {
+        set_last_error("gemm: operand strides must be multiples of 8 elements (ld=%lld sb1=%lld sb2=%lld)",
+                       (long long)op.ld, (long long)op.sb1, (long long)op.sb2);
+        return LD_ERR_ALIGNMENT;
+    }
+    const uint64_t inner = op.mn_major ? (uint64_t)rows : (uint64_t)K;
+    const uint64_t outer = op.mn_major ? (uint64_t)K : (uint64_t)rows;
+    if ((uint64_t)op.ld < inner && outer > 1) { set_last_error("gemm: ld (%lld) smaller than contiguous extent (%llu)", (long long)op.ld, (unsigned long long)inner); return LD_ERR_INVALID_ARG; }
+    const uint64_t dummy = 16;
+    uint64_t dims[4] = {inner, outer, (uint64_t)nb2, (uint64_t)nb1};
+    uint64_t strides[3] = {(uint64_t)op.ld * 2,
+                           nb2 > 1 ? (uint64_t)op.sb2 * 2 : dummy,
+                           nb1 > 1 ? (uint64_t)op.sb1 * 2 : dummy};
+    if (outer == 1 && strides[0] == 0) strides[0] = dummy;
+    for (int i = 0; i < 3; ++i) if (strides[i] == 0) { set_last_error("gemm: zero stride for a batched dimension"); return LD_ERR_INVALID_ARG; }
+    const uint32_t box_outer = op.mn_major ? (uint32_t)BK : (uint32_t)box_rows;
+    return encode_tmap_bf16_4d(tm, op.ptr, dims, strides, 64, box_outer);
+}
+
+}  // namespace
+
+extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
+    using namespace ld;
+    LD_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+    LD_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->nb1 > 0 && d->nb2 > 0, "gemm: non-positive dims M=%d N=%d K=%d nb=%dx%d", d->M, d->N, d->K, d->nb1, d->nb2);
+    LD_CHECK_ARG(d->D != nullptr, "gemm: null output");
+    LD_CHECK_ARG(d->split_k >= 1, "gemm: split_k must be >= 1");
+    LD_CHECK_ARG(d->split_k == 1 || (d->accumulate == 2 && d->d_dtype == LD_F32 && d->act == LD_ACT_NONE && !d->aux && !d->R && !d->col_bias),
+                 "gemm: split_k > 1 needs accumulate=2, fp32 output and a linear epilogue");
+    LD_CHECK_ARG(d->accumulate != 2 || d->d_dtype == LD_F32, "gemm: atomic accumulation needs fp32 output");
+    LD_CHECK_ARG(d->d_dtype == LD_F32 || d->d_dtype == LD_BF16, "gemm: bad d_dtype %d", d->d_dtype);
+    LD_CHECK_ARG(d->block_n == 0 || d->block_n == 128 || d->block_n == 256, "gemm: block_n must be 0/128/256");
+
+    KParams p{};
+    p.M = d->M; p.N = d->N; p.K = d->K; p.nb1 = d->nb1; p.nb2 = d->nb2;
+    p.act = d->act; p.accumulate = d->accumulate; p.split_k = d->split_k;
+    p.d_dtype = d->d_dtype; p.r_dtype = d->r_dtype;
+    p.a_mn = d->A.mn_major ? 1 : 0; p.b_mn = d->B.mn_major ? 1 : 0;
+    p.alpha = d->alpha; p.post_gain = d->post_gain;
+    p.D = d->D; p.ldd = d->ldd; p.d_sb1 = d->d_sb1; p.d_sb2 = d->d_sb2;
+    p.aux = d->aux;
+    p.R = d->R; p.ldr = d->ldr; p.r_sb1 = d->r_sb1; p.r_sb2 = d->r_sb2;
+    p.cs = d->col_scale; p.cb = d->col_bias; p.col_sb1 = d->col_sb1; p.col_sb2 = d->col_sb2;
+
+    const int sms = sm_count();
+    p.m_tiles = ceil_div(p.M, BM);
+    const long nb = (long)p.nb1 * p.nb2;
+    int bn = d->block_n;
+    if (bn == 0) {
+        const long tiles256 = nb * p.m_tiles * ceil_div(p.N, 256) * p.split_k;
+        bn = (p.N > 128 && tiles256 >= sms) ? 256 : 128;
+    }
+    p.bn = bn;
+    p.n_tiles = ceil_div(p.N, bn);
+    p.kb_total = ceil_div(p.K, BK);
+    if (p.split_k > p.kb_total) p.split_k = p.kb_total;
+    p.kb_per_split = ceil_div(p.kb_total, p.split_k);
+    p.split_k = ceil_div(p.kb_total, p.kb_per_split);     // no empty splits
+    const long total = nb * p.m_tiles * p.n_tiles * p.split_k;
+    LD_CHECK_ARG(total < (1L << 30), "gemm: too many tiles");
+    p.total_tiles = (int)total;
+
+    // vectorised epilogue needs 16-byte aligned rows for D / aux / R
+    const int d_es = p.d_dtype == LD_BF16 ? 2 : 4;
+    auto aligned = [](const void* ptr, long ld, long s1, long s2, int es) {
+        const long q = 16 / es;
+        return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % q == 0 && s1 % q == 0 && s2 % q == 0;
+    };
+    p.vec_ok = aligned(p.D, p.ldd, p.d_sb1, p.d_sb2, d_es) ? 1 : 0;
+    if (p.aux && !aligned(p.aux, p.ldd, p.d_sb1, p.d_sb2, d_es)) p.vec_ok = 0;
+    if (p.R && !aligned(p.R, p.ldr, p.r_sb1, p.r_sb2, p.r_dtype == LD_BF16 ? 2 : 4)) p.vec_ok = 0;
+
+    alignas(64) CUtensorMap tmA, tmB;
+    int e = make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
+    if (e) return e;
+    e = make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, bn);
+    if (e) return e;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        int s = cuda_status(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "gemm: set smem attr");
+        if (s) return s;
+        attr_set = true;
+    }
+    const int grid = (int)(total < sms ? total : sms);
+    gemm_bf16_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    count_launch();
+    LD_LAUNCH_CHECK("gemm launch");
+    return 0;
+}

@@ -1,0 +1,273 @@
+"""Tensor -> raw-pointer wrappers over the C-ABI in include/layoutdetr_sm100.h.
+
+PyTorch is used here only for device memory (caching allocator) and the current stream; every
+function launches hand-written sm_100a kernels from liblayoutdetr_sm100.so.  No fallbacks.
+"""
+import ctypes
+from ctypes import c_void_p, c_int, c_int32, c_int64, c_float
+
+import torch
+
+from ._lib import lib, check
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("unsupported dtype %s (fp32 / bf16 only)" % t.dtype)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("layoutdetr_b200 kernels need CUDA tensors (no CPU fallback); got %s" % t.device)
+
+
+class _Operand(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("ld", c_int64), ("sb1", c_int64), ("sb2", c_int64),
+                ("mn_major", c_int32), ("_pad", c_int32)]
+
+
+class _GemmDesc(ctypes.Structure):
+    _fields_ = [("M", c_int32), ("N", c_int32), ("K", c_int32), ("nb1", c_int32), ("nb2", c_int32),
+                ("act", c_int32), ("accumulate", c_int32), ("split_k", c_int32),
+                ("d_dtype", c_int32), ("r_dtype", c_int32), ("block_n", c_int32), ("_pad", c_int32),
+                ("alpha", c_float), ("post_gain", c_float),
+                ("A", _Operand), ("B", _Operand),
+                ("D", c_void_p), ("ldd", c_int64), ("d_sb1", c_int64), ("d_sb2", c_int64),
+                ("aux", c_void_p),
+                ("R", c_void_p), ("ldr", c_int64), ("r_sb1", c_int64), ("r_sb2", c_int64),
+                ("col_scale", c_void_p), ("col_bias", c_void_p), ("col_sb1", c_int64), ("col_sb2", c_int64)]
+
+
+class Op:
+    """A GEMM operand view: base tensor (bf16) + element offset, leading dim, batch strides, major-ness."""
+    __slots__ = ("t", "off", "ld", "sb1", "sb2", "mn")
+
+    def __init__(self, t, ld, off=0, sb1=0, sb2=0, mn=False):
+        self.t, self.off, self.ld, self.sb1, self.sb2, self.mn = t, off, ld, sb1, sb2, mn
+
+    def fill(self, o):
+        if self.t.dtype != torch.bfloat16:
+            raise TypeError("GEMM operands must be bf16")
+        o.ptr = self.t.data_ptr() + 2 * self.off
+        o.ld, o.sb1, o.sb2, o.mn_major = self.ld, self.sb1, self.sb2, 1 if self.mn else 0
+
+
+class Out:
+    """Output / residual view: tensor + element offset, leading dim, batch strides."""
+    __slots__ = ("t", "off", "ld", "sb1", "sb2")
+
+    def __init__(self, t, ld, off=0, sb1=0, sb2=0):
+        self.t, self.off, self.ld, self.sb1, self.sb2 = t, off, ld, sb1, sb2
+
+    def ptr(self):
+        return self.t.data_ptr() + self.t.element_size() * self.off
+
+
+def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0, accumulate=0, split_k=1,
+         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0):
+    """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics."""
+    _cuda(A.t, B.t, D.t)
+    d = _GemmDesc()
+    d.M, d.N, d.K, d.nb1, d.nb2 = M, N, K, nb1, nb2
+    d.act, d.accumulate, d.split_k = act, accumulate, split_k
+    d.d_dtype = dt(D.t)
+    d.block_n = block_n
+    d.alpha, d.post_gain = alpha, post_gain
+    A.fill(d.A)
+    B.fill(d.B)
+    d.D, d.ldd, d.d_sb1, d.d_sb2 = D.ptr(), D.ld, D.sb1, D.sb2
+    if aux is not None:
+        if aux.dtype != D.t.dtype:
+            raise TypeError("aux must have the dtype of D")
+        d.aux = aux.data_ptr() + aux.element_size() * D.off
+    if R is not None:
+        d.R, d.r_dtype, d.ldr, d.r_sb1, d.r_sb2 = R.ptr(), dt(R.t), R.ld, R.sb1, R.sb2
+    if col_scale is not None:
+        assert col_scale.dtype == torch.float32
+        d.col_scale = col_scale.data_ptr()
+    if col_bias is not None:
+        assert col_bias.dtype == torch.float32
+        d.col_bias = col_bias.data_ptr()
+    d.col_sb1, d.col_sb2 = col_sb1, col_sb2
+    check(lib().ld_gemm_bf16(ctypes.byref(d), _stream()), "ld_gemm_bf16")
+
+
+def linear(x, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None, aux=None,
+           alpha=1.0, post_gain=1.0, col_scale=None):
+    """y[M, N] = act(x[M, K] @ w[N, K]^T * col_scale + bias + residual).  x, w bf16 row-major (K % 8 == 0)."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    R = None
+    if residual is not None:
+        assert residual.shape == (M, N) and residual.stride(1) == 1
+        R = Out(residual, residual.stride(0))
+    gemm(M, N, K, Op(x, x.stride(0)), Op(w, w.stride(0)), Out(out, out.stride(0)), act=act, R=R,
+         col_bias=bias, col_scale=col_scale, aux=aux, alpha=alpha, post_gain=post_gain)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=False):
+    _cuda(x, gamma, beta)
+    rows, C = x.shape
+    assert x.stride(1) == 1
+    y16 = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if out_bf16 else None
+    y32 = torch.empty((rows, C), dtype=torch.float32, device=x.device) if out_f32 else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    check(lib().ld_layernorm_fwd(_p(x), c_int(dt(x)), c_int64(x.stride(0)), _p(gamma), _p(beta), _p(y16), _p(y32),
+                                 c_int64(C), _p(mean), _p(rstd), c_int(rows), c_int(C), c_float(eps), _stream()),
+          "ld_layernorm_fwd")
+    return y16, y32, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=None, dbeta=None, out_dtype=torch.bfloat16):
+    _cuda(dy, x, mean, rstd, gamma)
+    rows, C = x.shape
+    dx = torch.empty((rows, C), dtype=out_dtype, device=x.device)
+    dx16 = dx if out_dtype == torch.bfloat16 else None
+    dx32 = dx if out_dtype == torch.float32 else None
+    check(lib().ld_layernorm_bwd(_p(dy), c_int(dt(dy)), c_int64(dy.stride(0)), _p(x), c_int(dt(x)), c_int64(x.stride(0)),
+                                 _p(mean), _p(rstd), _p(gamma), _p(dx16), _p(dx32), c_int64(C), _p(dgamma), _p(dbeta),
+                                 c_int(rows), c_int(C), _stream()), "ld_layernorm_bwd")
+    return dx
+
+
+def embed_ln_fwd(ids, word, pos, gamma, beta, T, eps, save=False):
+    _cuda(ids, word, pos)
+    rows = ids.numel()
+    C = word.shape[1]
+    y = torch.empty((rows, C), dtype=torch.bfloat16, device=word.device)
+    pre = torch.empty((rows, C), dtype=torch.float32, device=word.device) if save else None
+    mean = torch.empty(rows, dtype=torch.float32, device=word.device) if save else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=word.device) if save else None
+    check(lib().ld_embed_ln_fwd(_p(ids), _p(word), _p(pos), _p(gamma), _p(beta), _p(y), _p(pre), _p(mean), _p(rstd),
+                                c_int(rows), c_int(T), c_int(C), c_float(eps), _stream()), "ld_embed_ln_fwd")
+    return y, pre, mean, rstd
+
+
+def embed_bwd(ids, dpre, dword, dpos, T, pad_id):
+    rows, C = dpre.shape
+    check(lib().ld_embed_bwd(_p(ids), _p(dpre), _p(dword), _p(dpos), c_int64(rows), c_int(T), c_int(C), c_int64(pad_id),
+                             _stream()), "ld_embed_bwd")
+
+
+def softmax_fwd(S, P, nb1, nb2, rows, cols, scale, key_mask=None, mask_inf=False, causal=False):
+    """S fp32 [nb1*nb2, rows, ldS] -> P bf16 [nb1*nb2, rows, ldP] (both contiguous 3-D tensors)."""
+    _cuda(S, P)
+    check(lib().ld_softmax_fwd(_p(S), c_int64(S.stride(1)), c_int64(S.stride(0)), _p(P), c_int64(P.stride(1)),
+                               c_int64(P.stride(0)), c_int(nb1), c_int(nb2), c_int(rows), c_int(cols), c_float(scale),
+                               _p(key_mask), c_int(1 if mask_inf else 0), c_int(1 if causal else 0), _stream()),
+          "ld_softmax_fwd")
+
+
+def softmax_bwd(P, dP, dS, nb, rows, cols, scale):
+    check(lib().ld_softmax_bwd(_p(P), c_int64(P.stride(1)), c_int64(P.stride(0)), _p(dP), c_int64(dP.stride(1)),
+                               c_int64(dP.stride(0)), _p(dS), c_int64(dS.stride(1)), c_int64(dS.stride(0)),
+                               c_int(nb), c_int(rows), c_int(cols), c_float(scale), _stream()), "ld_softmax_bwd")
+
+
+def cross_entropy(logits, labels, label_smoothing=0.0, ignore_index=-100, want_loss=True, dlogits=None, grad_scale=1.0):
+    _cuda(logits, labels)
+    rows, V = logits.shape
+    loss_rows = torch.empty(rows, dtype=torch.float32, device=logits.device) if want_loss else None
+    g_dt = dt(dlogits) if dlogits is not None else BF16
+    ldg = dlogits.stride(0) if dlogits is not None else 0
+    check(lib().ld_cross_entropy(_p(logits), c_int(dt(logits)), c_int64(logits.stride(0)), _p(labels), _p(loss_rows),
+                                 _p(dlogits), c_int(g_dt), c_int64(ldg), c_int64(rows), c_int(V),
+                                 c_float(label_smoothing), c_int64(ignore_index), c_float(grad_scale), _stream()),
+          "ld_cross_entropy")
+    return loss_rows
+
+
+# ------------------------------------------------------------------------------------------------
+def bias_act_raw(x, b, xref, yref, dy, y, grad, act_idx, alpha, gain, clamp, sizeB, stepB):
+    _cuda(x, y)
+    check(lib().ld_bias_act(_p(x), _p(b), _p(xref), _p(yref), _p(dy), _p(y), c_int(dt(x)), c_int(grad), c_int(act_idx),
+                            c_float(alpha), c_float(gain), c_float(clamp), c_int64(x.numel()), c_int(sizeB),
+                            c_int64(stepB), _stream()), "ld_bias_act")
+
+
+def fma_f32(a, b, c, y, b_period, b_div, c_period, c_div):
+    check(lib().ld_fma_f32(_p(a), _p(b), _p(c), _p(y), c_int64(a.numel()), c_int64(b_period), c_int64(b_div),
+                           c_int64(c_period), c_int64(c_div), _stream()), "ld_fma_f32")
+
+
+def cast_pad(src, dst_dtype, cols_dst=None):
+    """2-D cast with optional zero padding of the inner dim (to a multiple of 8 for TMA)."""
+    _cuda(src)
+    rows, cols = src.shape
+    assert src.stride(1) == 1
+    cols_dst = cols if cols_dst is None else cols_dst
+    dst = torch.empty((rows, cols_dst), dtype=dst_dtype, device=src.device)
+    check(lib().ld_cast_pad(_p(src), c_int(dt(src)), c_int64(src.stride(0)), _p(dst), c_int(dt(dst)), c_int64(cols_dst),
+                            c_int64(rows), c_int(cols), c_int(cols_dst), _stream()), "ld_cast_pad")
+    return dst
+
+
+def to_bf16(x):
+    """Contiguous fp32 -> bf16 copy (any shape)."""
+    if x.dtype == torch.bfloat16:
+        return x
+    x = x.contiguous()
+    out = cast_pad(x.view(1, -1), torch.bfloat16)
+    return out.view(x.shape)
+
+
+def to_f32(x):
+    if x.dtype == torch.float32:
+        return x
+    x = x.contiguous()
+    return cast_pad(x.view(1, -1), torch.float32).view(x.shape)
+
+
+def axpby_bcast(a, b, out_dtype=torch.bfloat16, alpha=1.0, beta=1.0):
+    """out = alpha * a + beta * b, with b broadcast periodically over a (a.numel() % b.numel() == 0)."""
+    _cuda(a, b)
+    a = a.contiguous(); b = b.contiguous()
+    assert a.numel() % b.numel() == 0
+    out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
+    check(lib().ld_axpby_bcast(_p(a), c_int(dt(a)), _p(b), c_int(dt(b)), _p(out), c_int(dt(out)), c_int64(a.numel()),
+                               c_int64(b.numel()), c_float(alpha), c_float(beta), _stream()), "ld_axpby_bcast")
+    return out
+
+
+def act_bwd(dy, ref, act, gain=1.0):
+    dy = dy.contiguous(); ref = ref.contiguous()
+    dx = torch.empty_like(dy)
+    check(lib().ld_act_bwd(_p(dy), c_int(dt(dy)), _p(ref), c_int(dt(ref)), _p(dx), c_int(dt(dx)), c_int64(dy.numel()),
+                           c_int(act), c_float(gain), _stream()), "ld_act_bwd")
+    return dx
+
+
+def colsum_accum(x, out):
+    """out[c] += sum_r x[r, c]  (bias gradients)."""
+    rows, cols = x.shape
+    check(lib().ld_colsum_accum(_p(x), c_int(dt(x)), c_int64(x.stride(0)), _p(out), c_int64(rows), c_int(cols), _stream()),
+          "ld_colsum_accum")
+
+
+def scale_channels(x, s, out_dtype, per_sample, C):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    check(lib().ld_scale_channels(_p(x), c_int(dt(x)), _p(s), _p(y), c_int(dt(y)), c_int64(x.numel()), c_int64(per_sample),
+                                  c_int(C), _stream()), "ld_scale_channels")
+    return y

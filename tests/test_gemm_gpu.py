@@ -1,0 +1,123 @@
+"""tcgen05 GEMM parity on the GPU: every operand-major combination, tails, batching, epilogues.
+Reference = fp32 matmul of the same bf16-rounded inputs (tolerance: bf16 inputs are exact in the
+reference, fp32 accumulation order differs -> 2e-3 relative to the output scale)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _check(out, ref, tol=2e-3, what=""):
+    scale = ref.abs().max().item() + 1e-6
+    err = (out.float() - ref).abs().max().item() / scale
+    assert err < tol, "%s: rel err %.3e (scale %.3e)" % (what, err, scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (300, 200, 136), (1024, 768, 768),
+                                   (9, 8, 40), (4096, 3072, 768), (144, 30524, 768)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    from layoutdetr_b200 import kernels as k
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operand needs ld % 8 == 0")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = _rand((M, K), g)
+    B = _rand((N, K), g)
+    ref = A.float() @ B.float().t()
+    At = A.t().contiguous() if a_mn else A
+    Bt = B.t().contiguous() if b_mn else B
+    D = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    k.gemm(M, N, K, k.Op(At, At.stride(0), mn=a_mn), k.Op(Bt, Bt.stride(0), mn=b_mn), k.Out(D, N))
+    torch.cuda.synchronize()
+    _check(D, ref, what="gemm M%d N%d K%d a_mn=%s b_mn=%s" % (M, N, K, a_mn, b_mn))
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_epilogue(block_n):
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 520, 392, 264
+    A, B = _rand((M, K), g, 0.5), _rand((N, K), g, 0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    scale = torch.rand(N, generator=g, device="cuda") + 0.5
+    R = _rand((M, N), g)
+    pre = (A.float() @ B.float().t()) * 0.5 * scale + bias + R.float()
+    for act, fn in [(k.ACT_NONE, lambda v: v), (k.ACT_RELU, torch.relu),
+                    (k.ACT_GELU, torch.nn.functional.gelu), (k.ACT_LRELU, lambda v: torch.nn.functional.leaky_relu(v, 0.2)),
+                    (k.ACT_SIGMOID, torch.sigmoid)]:
+        D = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+        aux = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+        k.gemm(M, N, K, k.Op(A, K), k.Op(B, K), k.Out(D, N), alpha=0.5, act=act, post_gain=1.5, R=k.Out(R, N),
+               col_scale=scale, col_bias=bias, aux=aux, block_n=block_n)
+        torch.cuda.synchronize()
+        _check(D, fn(pre) * 1.5, tol=1e-2, what="epilogue act %d" % act)
+        _check(aux, pre, tol=1e-2, what="aux act %d" % act)
+
+
+def test_gemm_batched_strided_attention_layout():
+    """Q K^T and P V straight from a fused [B*T, 3*H*d] QKV buffer with two batch dims."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Bn, T, H, d = 3, 256, 4, 192
+    qkv = _rand((Bn * T, 3 * H * d), g, 0.3)
+    ld = 3 * H * d
+    S = torch.empty((Bn * H, T, T), dtype=torch.float32, device="cuda")
+    k.gemm(T, T, d, k.Op(qkv, ld, off=0, sb1=T * ld, sb2=d), k.Op(qkv, ld, off=H * d, sb1=T * ld, sb2=d),
+           k.Out(S, T, sb1=H * T * T, sb2=T * T), nb1=Bn, nb2=H, alpha=0.125)
+    q = qkv[:, :H * d].float().view(Bn, T, H, d).permute(0, 2, 1, 3)
+    kk = qkv[:, H * d:2 * H * d].float().view(Bn, T, H, d).permute(0, 2, 1, 3)
+    v = qkv[:, 2 * H * d:].float().view(Bn, T, H, d).permute(0, 2, 1, 3)
+    ref = (q @ kk.transpose(-1, -2)) * 0.125
+    torch.cuda.synchronize()
+    _check(S.view(Bn, H, T, T), ref, what="QK^T")
+    P = torch.softmax(ref, -1).to(torch.bfloat16).contiguous().view(Bn * H, T, T)
+    O = torch.empty((Bn * T, H * d), dtype=torch.bfloat16, device="cuda")
+    k.gemm(T, d, T, k.Op(P, T, sb1=H * T * T, sb2=T * T), k.Op(qkv, ld, off=2 * H * d, sb1=T * ld, sb2=d, mn=True),
+           k.Out(O, H * d, sb1=T * H * d, sb2=d), nb1=Bn, nb2=H)
+    refO = (P.float().view(Bn, H, T, T) @ v).permute(0, 2, 1, 3).reshape(Bn * T, H * d)
+    torch.cuda.synchronize()
+    _check(O, refO, tol=1e-2, what="PV")
+
+
+def test_gemm_small_keys():
+    """DETR decoder shapes: 9/10 keys, head_dim 32 (K tails below one 64-wide k-block)."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(13)
+    Bn, L, H, d = 5, 10, 8, 32
+    q = _rand((Bn * L, H * d), g); kk = _rand((Bn * L, H * d), g); v = _rand((Bn * L, H * d), g)
+    S = torch.empty((Bn * H, L, L), dtype=torch.float32, device="cuda")
+    k.gemm(L, L, d, k.Op(q, H * d, sb1=L * H * d, sb2=d), k.Op(kk, H * d, sb1=L * H * d, sb2=d),
+           k.Out(S, L, sb1=H * L * L, sb2=L * L), nb1=Bn, nb2=H)
+    qf = q.float().view(Bn, L, H, d).permute(0, 2, 1, 3); kf = kk.float().view(Bn, L, H, d).permute(0, 2, 1, 3)
+    vf = v.float().view(Bn, L, H, d).permute(0, 2, 1, 3)
+    torch.cuda.synchronize()
+    _check(S.view(Bn, H, L, L), qf @ kf.transpose(-1, -2), what="small QK^T")
+    Lp = 16
+    P = torch.zeros((Bn * H, L, Lp), dtype=torch.bfloat16, device="cuda")
+    P[:, :, :L] = torch.softmax(S, -1).to(torch.bfloat16)
+    O = torch.empty((Bn * L, H * d), dtype=torch.bfloat16, device="cuda")
+    k.gemm(L, d, L, k.Op(P, Lp, sb1=H * L * Lp, sb2=L * Lp), k.Op(v, H * d, sb1=L * H * d, sb2=d, mn=True),
+           k.Out(O, H * d, sb1=L * H * d, sb2=d), nb1=Bn, nb2=H)
+    refO = (P[:, :, :L].float().view(Bn, H, L, L) @ vf).permute(0, 2, 1, 3).reshape(Bn * L, H * d)
+    torch.cuda.synchronize()
+    _check(O, refO, tol=1e-2, what="small PV")
+
+
+def test_gemm_splitk_accumulate():
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(17)
+    M, N, K = 768, 768, 8192     # wgrad-like: long K, few tiles
+    At = _rand((K, M), g, 0.2); Bt = _rand((K, N), g, 0.2)
+    base = torch.randn((M, N), generator=g, device="cuda")
+    D = base.clone()
+    k.gemm(M, N, K, k.Op(At, M, mn=True), k.Op(Bt, N, mn=True), k.Out(D, N), accumulate=2, split_k=8)
+    torch.cuda.synchronize()
+    _check(D, base + At.float().t() @ Bt.float(), what="split-k")
+    D2 = base.clone()
+    k.gemm(M, N, K, k.Op(At, M, mn=True), k.Op(Bt, N, mn=True), k.Out(D2, N), accumulate=1)
+    torch.cuda.synchronize()
+    _check(D2, base + At.float().t() @ Bt.float(), what="accumulate=1")

@@ -1,0 +1,119 @@
+"""Bytes-bound kernels vs plain PyTorch fp32 references on the GPU (LayerNorm, softmax, CE, casts)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("C", [256, 768])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(C, dtype):
+    from layoutdetr_b200 import kernels as k
+    g = _gen(C)
+    rows = 1000
+    x = (torch.randn((rows, C), generator=g, device="cuda") * 2 + 0.3).to(dtype)
+    gamma = torch.rand(C, generator=g, device="cuda") + 0.5
+    beta = torch.randn(C, generator=g, device="cuda")
+    y16, y32, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-5, out_bf16=True, out_f32=True, save_stats=True)
+    xr = x.float().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    torch.testing.assert_close(y32, ref, atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(y16.float(), ref, atol=3e-2, rtol=1e-2)
+    dy = torch.randn((rows, C), generator=g, device="cuda")
+    ref.backward(dy)
+    dgamma = torch.zeros(C, device="cuda"); dbeta = torch.zeros(C, device="cuda")
+    dx = k.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, out_dtype=torch.float32)
+    torch.testing.assert_close(dx, xr.grad, atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(dgamma, gr.grad, atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(dbeta, br.grad, atol=2e-3, rtol=1e-4)
+
+
+def test_embed_ln():
+    from layoutdetr_b200 import kernels as k
+    g = _gen(3)
+    V, T, C, n = 1000, 16, 768, 5
+    word = torch.randn((V, C), generator=g, device="cuda") * 0.02
+    pos = torch.randn((512, C), generator=g, device="cuda") * 0.02
+    gamma = torch.rand(C, generator=g, device="cuda") + 0.5
+    beta = torch.randn(C, generator=g, device="cuda") * 0.1
+    ids = torch.randint(0, V, (n, T), generator=g, device="cuda")
+    y, pre, mean, rstd = k.embed_ln_fwd(ids, word, pos, gamma, beta, T, 1e-12, save=True)
+    ref_pre = word[ids] + pos[:T][None]
+    ref = F.layer_norm(ref_pre, (C,), gamma, beta, 1e-12)
+    torch.testing.assert_close(pre.view(n, T, C), ref_pre, atol=1e-7, rtol=0)
+    torch.testing.assert_close(y.float().view(n, T, C), ref, atol=3e-2, rtol=1e-2)
+    dword = torch.zeros_like(word); dpos = torch.zeros_like(pos)
+    dpre = torch.randn((n * T, C), generator=g, device="cuda")
+    k.embed_bwd(ids, dpre, dword, dpos, T, pad_id=0)
+    ref_dword = torch.zeros_like(word).index_add_(0, ids.view(-1), dpre)
+    ref_dword[0] = 0
+    torch.testing.assert_close(dword, ref_dword, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(dpos[:T], dpre.view(n, T, C).sum(0), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("cols,mask_inf,causal", [(256, False, False), (256, False, True), (64, True, False), (10, True, False)])
+def test_softmax(cols, mask_inf, causal):
+    from layoutdetr_b200 import kernels as k
+    g = _gen(cols)
+    nb1, nb2, rows = 3, 4, cols
+    ldp = (cols + 7) // 8 * 8
+    S = torch.randn((nb1 * nb2, rows, cols), generator=g, device="cuda") * 3
+    km = torch.zeros((nb1, cols), dtype=torch.uint8, device="cuda")
+    km[0, cols // 2:] = 1; km[2, -1] = 1
+    P = torch.zeros((nb1 * nb2, rows, ldp), dtype=torch.bfloat16, device="cuda")
+    k.softmax_fwd(S, P, nb1, nb2, rows, cols, 0.3, key_mask=km, mask_inf=mask_inf, causal=causal)
+    add = torch.zeros((nb1, 1, rows, cols), device="cuda")
+    neg = float("-inf") if mask_inf else -10000.0
+    add = add.masked_fill(km.bool()[:, None, None, :], neg)
+    if causal:
+        cm = torch.ones(rows, cols, device="cuda").triu(1).bool()
+        add = add.masked_fill(cm[None, None], neg)
+    ref = torch.softmax(S.view(nb1, nb2, rows, cols) * 0.3 + add, -1).view(nb1 * nb2, rows, cols)
+    torch.testing.assert_close(P[:, :, :cols].float(), ref, atol=4e-3, rtol=1e-2)
+    dP = torch.randn((nb1 * nb2, rows, cols), generator=g, device="cuda")
+    dS = torch.zeros_like(P)
+    k.softmax_bwd(P, dP, dS, nb1 * nb2, rows, cols, 0.3)
+    Pf = P[:, :, :cols].float()
+    ref_dS = Pf * (dP - (dP * Pf).sum(-1, keepdim=True)) * 0.3
+    torch.testing.assert_close(dS[:, :, :cols].float(), ref_dS, atol=1e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("V,eps,dtype", [(30524, 0.1, torch.bfloat16), (256, 0.0, torch.float32), (8, 0.0, torch.float32)])
+def test_cross_entropy(V, eps, dtype):
+    from layoutdetr_b200 import kernels as k
+    g = _gen(V)
+    rows = 300
+    logits = (torch.randn((rows, V), generator=g, device="cuda") * 2).to(dtype)
+    labels = torch.randint(0, V, (rows,), generator=g, device="cuda")
+    labels[::7] = -100
+    n_valid = int((labels != -100).sum())
+    dl = torch.empty((rows, V), dtype=dtype, device="cuda")
+    loss_rows = k.cross_entropy(logits, labels, eps, -100, True, dl, grad_scale=1.0 / n_valid)
+    lr = logits.float().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels, label_smoothing=eps, ignore_index=-100)
+    ref.backward()
+    torch.testing.assert_close(loss_rows.sum() / n_valid, ref, atol=1e-4, rtol=1e-4)
+    tol = 1e-6 if dtype == torch.float32 else 2e-5
+    torch.testing.assert_close(dl.float(), lr.grad, atol=tol, rtol=2e-2)
+
+
+def test_cast_and_axpby():
+    from layoutdetr_b200 import kernels as k
+    g = _gen(9)
+    x = torch.randn((37, 36), generator=g, device="cuda")
+    y = k.cast_pad(x, torch.bfloat16, 40)
+    assert y.shape == (37, 40)
+    torch.testing.assert_close(y[:, :36], x.to(torch.bfloat16), atol=0, rtol=0)
+    assert float(y[:, 36:].abs().max()) == 0.0
+    a = torch.randn((4, 64, 256), generator=g, device="cuda").to(torch.bfloat16)
+    b = torch.randn((64, 256), generator=g, device="cuda")
+    out = k.axpby_bcast(a, b, torch.bfloat16)
+    torch.testing.assert_close(out.float(), (a.float() + b[None]).to(torch.bfloat16).float(), atol=0, rtol=0)
+    z = torch.randn((1024, 1024), generator=g, device="cuda")
+    torch.testing.assert_close(k.to_bf16(z), z.to(torch.bfloat16), atol=0, rtol=0)
