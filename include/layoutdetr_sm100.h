@@ -46,7 +46,7 @@ void ld_launch_count_reset(void);
  *
  *   for every batch (b1, b2):
  *     acc[m, n] = sum_k A[m, k] * B[n, k]                         (fp32 accumulation)
- *     v   = acc * alpha
+ *     v   = acc * alpha * (alpha_dev ? *alpha_dev : 1)
  *     v   = v * col_scale[n]   (if col_scale)   + col_bias[n] (if col_bias)
  *     v  += R[m, n]            (if R)
  *     aux[m, n] = v            (if aux; pre-activation, dtype of D)
@@ -89,6 +89,7 @@ typedef struct ld_gemm_desc {
     const void* R;  int64_t ldr, r_sb1, r_sb2;
     const float* col_scale; const float* col_bias;
     int64_t col_sb1, col_sb2;    /* batch strides of col_scale/col_bias (0 = shared) */
+    const float* alpha_dev;      /* optional device scalar multiplied into alpha (upstream loss gradient) */
 } ld_gemm_desc;
 
 int ld_gemm_bf16(const ld_gemm_desc* desc, void* stream);

@@ -205,17 +205,30 @@ int ld_bias_act(const void* x, const void* b, const void* xref, const void* yref
     return 0;
 }
 
-// fma(a, b, c) = a * b + c with b, c broadcast per (sample, channel) or full-size
-// (torch_utils/ops/fma.py:16; used by modulated_conv2d's demodulate+noise branch, networks_stylegan2.py:70)
-__global__ void fma_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ y,
-                           long n, long b_period, long b_div, long c_period, long c_div) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        y[i] = fmaf(a[i], b[(i / b_div) % b_period], c[(i / c_div) % c_period]);
+// fma(a, b, c) = a * b + c with numpy-style broadcasting of b and c against a contiguous 4-D `a`
+// (torch_utils/ops/fma.py:16; used by modulated_conv2d's demodulate+noise branch, networks_stylegan2.py:70).
+// b_strides / c_strides are element strides in a's index space, 0 on broadcast dims.
+struct FmaArgs { const float* a; const float* b; const float* c; float* y; long n; int d1, d2, d3; long bs[4], cs[4]; };
+__global__ void fma_kernel(FmaArgs p) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long)gridDim.x * blockDim.x) {
+        long t = i;
+        const int i3 = (int)(t % p.d3); t /= p.d3;
+        const int i2 = (int)(t % p.d2); t /= p.d2;
+        const int i1 = (int)(t % p.d1); const long i0 = t / p.d1;
+        const float bv = p.b[i0 * p.bs[0] + i1 * p.bs[1] + i2 * p.bs[2] + i3 * p.bs[3]];
+        const float cv = p.c[i0 * p.cs[0] + i1 * p.cs[1] + i2 * p.cs[2] + i3 * p.cs[3]];
+        p.y[i] = fmaf(p.a[i], bv, cv);
+    }
 }
-int ld_fma_f32(const float* a, const float* b, const float* c, float* y, int64_t n,
-               int64_t b_period, int64_t b_div, int64_t c_period, int64_t c_div, void* stream) {
-    LD_CHECK_ARG(a && b && c && y && n > 0 && b_period > 0 && b_div > 0 && c_period > 0 && c_div > 0, "fma: bad argument");
-    fma_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, y, n, b_period, b_div, c_period, c_div);
+int ld_fma_f32(const float* a, const float* b, const float* c, float* y, const int64_t* a_shape,
+               const int64_t* b_strides, const int64_t* c_strides, void* stream) {
+    LD_CHECK_ARG(a && b && c && y && a_shape && b_strides && c_strides, "fma: null pointer");
+    FmaArgs p; p.a = a; p.b = b; p.c = c; p.y = y;
+    p.n = a_shape[0] * a_shape[1] * a_shape[2] * a_shape[3];
+    LD_CHECK_ARG(p.n > 0, "fma: empty tensor");
+    p.d1 = (int)a_shape[1]; p.d2 = (int)a_shape[2]; p.d3 = (int)a_shape[3];
+    for (int i = 0; i < 4; ++i) { p.bs[i] = b_strides[i]; p.cs[i] = c_strides[i]; }
+    fma_kernel<<<ew_grid(p.n, 256), 256, 0, (cudaStream_t)stream>>>(p);
     ld::count_launch();
     LD_LAUNCH_CHECK("fma");
     return 0;
@@ -301,4 +314,106 @@ int ld_scale_channels(const void* x, int x_dtype, const float* s, void* y, int y
     return 0;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// StyleGAN2 modulated-conv epilogue on channels-last activations (reference
+// training/networks_stylegan2.py:66-75 + SynthesisLayer.forward :307-325, non-fused modconv path):
+//   y[b,p,c] = act(x[b,p,c] * d[b,c] + bias[c]) * gain          d = demodulation coefficients
+// and its backward:
+//   g = dy * gain * act'(y);  dx = g * d;  dd[b,c] += sum_p g * x;  dbias[c] += sum_p,b g
+// act: LD_ACT_NONE or LD_ACT_LRELU (slope 0.2).
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <typename TX>
+__global__ void demod_bias_act_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ d, const float* __restrict__ bias,
+                                          __nv_bfloat16* __restrict__ y, long n, long per_sample, int C, int act, float gain) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / per_sample; const int c = (int)(i % C);
+        float v = ldf<TX>(x, i);
+        if (d) v *= d[b * C + c];
+        if (bias) v += bias[c];
+        if (act == LD_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+        y[i] = f32_to_bf16(v * gain);
+    }
+}
+
+// one block handles a strip of pixels of one sample; channel partial sums in registers -> atomics
+template <typename TX>
+__global__ void __launch_bounds__(256)
+demod_bias_act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const TX* __restrict__ x,
+                          const float* __restrict__ d, __nv_bfloat16* __restrict__ dx, float* __restrict__ dd, float* __restrict__ dbias,
+                          long pixels, int C, int act, float gain, int pix_per_block) {
+    const int b = blockIdx.y;
+    const long p0 = (long)blockIdx.x * pix_per_block;
+    const long p1 = min(pixels, p0 + pix_per_block);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float dc = d ? d[(long)b * C + c] : 1.f;
+        float sd = 0.f, sb = 0.f;
+        for (long p = p0; p < p1; ++p) {
+            const long i = ((long)b * pixels + p) * C + c;
+            float g = bf16_to_f32(dy[i]) * gain;
+            if (act == LD_ACT_LRELU && bf16_to_f32(y[i]) < 0.f) g *= 0.2f;
+            sd += g * ldf<TX>(x, i);
+            sb += g;
+            dx[i] = f32_to_bf16(g * dc);
+        }
+        if (dd) atomicAdd(dd + (long)b * C + c, sd);
+        if (dbias) atomicAdd(dbias + c, sb);
+    }
+}
+
+// out[b,c] += sum_p a[b,p,c] * g[b,p,c]     (gradient of the per-sample style modulation x * s[b,c])
+template <typename TA>
+__global__ void __launch_bounds__(256)
+channel_dot_kernel(const TA* __restrict__ a, const __nv_bfloat16* __restrict__ g, float* __restrict__ out, long pixels, int C, int pix_per_block) {
+    const int b = blockIdx.y;
+    const long p0 = (long)blockIdx.x * pix_per_block;
+    const long p1 = min(pixels, p0 + pix_per_block);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (long p = p0; p < p1; ++p) {
+            const long i = ((long)b * pixels + p) * C + c;
+            s += ldf<TA>(a, i) * bf16_to_f32(g[i]);
+        }
+        atomicAdd(out + (long)b * C + c, s);
+    }
+}
+}  // namespace
+
+extern "C" {
+int ld_demod_bias_act_fwd(const void* x, int x_dtype, const float* d, const float* bias, void* y_bf16,
+                          int B, int64_t pixels, int C, int act, float gain, void* stream) {
+    LD_CHECK_ARG(x && y_bf16 && B > 0 && pixels > 0 && C > 0, "demod_bias_act_fwd: bad argument");
+    const long n = (long)B * pixels * C;
+    const int grid = ew_grid(n, 256);
+    if (x_dtype == LD_F32) demod_bias_act_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, d, bias, (__nv_bfloat16*)y_bf16, n, pixels * C, C, act, gain);
+    else demod_bias_act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, d, bias, (__nv_bfloat16*)y_bf16, n, pixels * C, C, act, gain);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("demod_bias_act_fwd");
+    return 0;
+}
+
+int ld_demod_bias_act_bwd(const void* dy_bf16, const void* y_bf16, const void* x, int x_dtype, const float* d,
+                          void* dx_bf16, float* dd, float* dbias, int B, int64_t pixels, int C, int act, float gain, void* stream) {
+    LD_CHECK_ARG(dy_bf16 && y_bf16 && x && dx_bf16 && B > 0 && pixels > 0 && C > 0, "demod_bias_act_bwd: bad argument");
+    const int ppb = (int)std::max<long>(1, std::min<long>(256, pixels / 4 + 1));
+    dim3 grid((unsigned)((pixels + ppb - 1) / ppb), (unsigned)B);
+    if (x_dtype == LD_F32) demod_bias_act_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy_bf16, (const __nv_bfloat16*)y_bf16, (const float*)x, d, (__nv_bfloat16*)dx_bf16, dd, dbias, pixels, C, act, gain, ppb);
+    else demod_bias_act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy_bf16, (const __nv_bfloat16*)y_bf16, (const __nv_bfloat16*)x, d, (__nv_bfloat16*)dx_bf16, dd, dbias, pixels, C, act, gain, ppb);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("demod_bias_act_bwd");
+    return 0;
+}
+
+int ld_channel_dot(const void* a, int a_dtype, const void* g_bf16, float* out, int B, int64_t pixels, int C, void* stream) {
+    LD_CHECK_ARG(a && g_bf16 && out && B > 0 && pixels > 0 && C > 0, "channel_dot: bad argument");
+    const int ppb = (int)std::max<long>(1, std::min<long>(256, pixels / 4 + 1));
+    dim3 grid((unsigned)((pixels + ppb - 1) / ppb), (unsigned)B);
+    if (a_dtype == LD_F32) channel_dot_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, (const __nv_bfloat16*)g_bf16, out, pixels, C, ppb);
+    else channel_dot_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)g_bf16, out, pixels, C, ppb);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("channel_dot");
+    return 0;
+}
 }  // extern "C"

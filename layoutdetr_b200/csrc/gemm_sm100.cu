@@ -39,6 +39,7 @@ struct KParams {
     void* aux;
     const void* R; long ldr, r_sb1, r_sb2;
     const float* cs; const float* cb; long col_sb1, col_sb2;
+    const float* alpha_dev;
 };
 
 struct Tile {
@@ -167,6 +168,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3;                       // TMEM lane quadrant of this warp
         int as = 0; uint32_t aphase = 0;
+        const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const Tile tl = decode_tile(p, t);
             mbar_wait(&tfull_bar[as], aphase);
@@ -186,7 +188,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (!row_ok) continue;
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * alpha;
                 const bool full_chunk = (n_base + 16 <= p.N);
                 if (p.cs) {
 #pragma unroll
@@ -344,6 +346,7 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     p.aux = d->aux;
     p.R = d->R; p.ldr = d->ldr; p.r_sb1 = d->r_sb1; p.r_sb2 = d->r_sb2;
     p.cs = d->col_scale; p.cb = d->col_bias; p.col_sb1 = d->col_sb1; p.col_sb2 = d->col_sb2;
+    p.alpha_dev = d->alpha_dev;
 
     const int sms = sm_count();
     p.m_tiles = ceil_div(p.M, BM);

@@ -1,0 +1,109 @@
+"""Host-side engine state: bf16 weight shadows, direct gradient accumulation, GEMM heuristics.
+
+The master parameters stay fp32 `nn.Parameter`s (the training loop reads / writes `.grad`, the
+optimizer updates them, `state_dict` keys match the reference).  Tensor cores read bf16 shadows that
+are refreshed lazily whenever a parameter's version counter changes (optimizer step, load_state_dict,
+EMA copy).
+"""
+import torch
+
+from . import kernels as K
+
+_shadow = {}          # (id(param), tag) -> (version, data_ptr, tensor)
+_SM_COUNT = None
+
+
+def sm_count():
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        _SM_COUNT = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _SM_COUNT
+
+
+def clear_cache():
+    _shadow.clear()
+
+
+def _lookup(key, params):
+    ent = _shadow.get(key)
+    if ent is None:
+        return None
+    ver = tuple(p._version for p in params)
+    ptr = tuple(p.data_ptr() for p in params)
+    if ent[0] == ver and ent[1] == ptr:
+        return ent[2]
+    return None
+
+
+def _store(key, params, value):
+    _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params), value)
+    return value
+
+
+def pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def w_bf16(param):
+    """bf16 shadow of a 2-D weight [N, K] with K zero-padded to a multiple of 8 (TMA stride rule)."""
+    key = (id(param), "w")
+    v = _lookup(key, (param,))
+    if v is None:
+        with torch.no_grad():
+            w = param.detach()
+            w2 = w.reshape(w.shape[0], -1)
+            v = K.cast_pad(w2, torch.bfloat16, pad8(w2.shape[1]))
+        _store(key, (param,), v)
+    return v
+
+
+def w_cat_bf16(params):
+    """bf16 shadow of several [Ni, K] weights concatenated along N (fused QKV projections)."""
+    key = (tuple(id(p) for p in params), "cat")
+    v = _lookup(key, params)
+    if v is None:
+        with torch.no_grad():
+            v = torch.cat([w_bf16(p) for p in params], dim=0)
+        _store(key, params, v)
+    return v
+
+
+def b_cat_f32(params):
+    key = (tuple(id(p) for p in params), "bcat")
+    v = _lookup(key, params)
+    if v is None:
+        with torch.no_grad():
+            v = torch.cat([p.detach().float() for p in params], dim=0).contiguous()
+        _store(key, params, v)
+    return v
+
+
+def derived(param_tuple, tag, fn):
+    """Cache an arbitrary tensor derived from parameters / buffers (e.g. folded FrozenBN scale+bias,
+    conv weights re-laid out as [Cout, kh*kw*Cin])."""
+    key = (tuple(id(p) for p in param_tuple), tag)
+    v = _lookup(key, param_tuple)
+    if v is None:
+        with torch.no_grad():
+            v = fn()
+        _store(key, param_tuple, v)
+    return v
+
+
+def grad_buffer(param):
+    """fp32 gradient accumulator of a parameter (created zeroed on first use).  Backward kernels add
+    straight into it (GEMM epilogue accumulate / atomics) instead of materialising a temporary that
+    autograd would add afterwards."""
+    if param.grad is None:
+        param.grad = torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format)
+    return param.grad
+
+
+def wgrad_split_k(M_out, N_out, K_red):
+    """Split-K factor for weight-gradient GEMMs (few output tiles, long reduction)."""
+    tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
+    kb = (K_red + 63) // 64
+    sms = sm_count()
+    if tiles >= sms or kb <= 8:
+        return 1
+    return int(max(1, min(kb // 4, (2 * sms) // tiles)))

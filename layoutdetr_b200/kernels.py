@@ -50,7 +50,8 @@ class _GemmDesc(ctypes.Structure):
                 ("D", c_void_p), ("ldd", c_int64), ("d_sb1", c_int64), ("d_sb2", c_int64),
                 ("aux", c_void_p),
                 ("R", c_void_p), ("ldr", c_int64), ("r_sb1", c_int64), ("r_sb2", c_int64),
-                ("col_scale", c_void_p), ("col_bias", c_void_p), ("col_sb1", c_int64), ("col_sb2", c_int64)]
+                ("col_scale", c_void_p), ("col_bias", c_void_p), ("col_sb1", c_int64), ("col_sb2", c_int64),
+                ("alpha_dev", c_void_p)]
 
 
 class Op:
@@ -79,7 +80,7 @@ class Out:
 
 
 def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0, accumulate=0, split_k=1,
-         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0):
+         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None):
     """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics."""
     _cuda(A.t, B.t, D.t)
     d = _GemmDesc()
@@ -104,6 +105,9 @@ def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0,
         assert col_bias.dtype == torch.float32
         d.col_bias = col_bias.data_ptr()
     d.col_sb1, d.col_sb2 = col_sb1, col_sb2
+    if alpha_dev is not None:
+        assert alpha_dev.dtype == torch.float32
+        d.alpha_dev = alpha_dev.data_ptr()
     check(lib().ld_gemm_bf16(ctypes.byref(d), _stream()), "ld_gemm_bf16")
 
 
@@ -206,16 +210,31 @@ def bias_act_raw(x, b, xref, yref, dy, y, grad, act_idx, alpha, gain, clamp, siz
                             c_int64(stepB), _stream()), "ld_bias_act")
 
 
-def fma_f32(a, b, c, y, b_period, b_div, c_period, c_div):
-    check(lib().ld_fma_f32(_p(a), _p(b), _p(c), _p(y), c_int64(a.numel()), c_int64(b_period), c_int64(b_div),
-                           c_int64(c_period), c_int64(c_div), _stream()), "ld_fma_f32")
+def fma_f32(a, b, c):
+    """a * b + c (fp32): a contiguous (<= 4-D), b / c broadcastable to a."""
+    _cuda(a, b, c)
+    shape = list(a.shape)
+    while len(shape) < 4:
+        shape = [1] + shape
+    a4 = a.contiguous().view(shape)
+    be = b.broadcast_to(a.shape)
+    ce = c.broadcast_to(a.shape)
+    pad = 4 - be.ndim
+    bs = (c_int64 * 4)(*([0] * pad + list(be.stride())))
+    cs = (c_int64 * 4)(*([0] * pad + list(ce.stride())))
+    sh = (c_int64 * 4)(*shape)
+    y = torch.empty_like(a4)
+    check(lib().ld_fma_f32(_p(a4), _p(be), _p(ce), _p(y), sh, bs, cs, _stream()), "ld_fma_f32")
+    return y.view(a.shape)
 
 
-def cast_pad(src, dst_dtype, cols_dst=None):
-    """2-D cast with optional zero padding of the inner dim (to a multiple of 8 for TMA)."""
+def cast_pad(src, dst_dtype, cols_dst=None, cols_src=None):
+    """2-D cast with optional zero padding (cols_dst > cols) or truncation (cols_src < src.shape[1]) of the
+    inner dim (padding to a multiple of 8 is what TMA needs)."""
     _cuda(src)
     rows, cols = src.shape
     assert src.stride(1) == 1
+    cols = cols if cols_src is None else cols_src
     cols_dst = cols if cols_dst is None else cols_dst
     dst = torch.empty((rows, cols_dst), dtype=dst_dtype, device=src.device)
     check(lib().ld_cast_pad(_p(src), c_int(dt(src)), c_int64(src.stride(0)), _p(dst), c_int(dt(dst)), c_int64(cols_dst),
@@ -271,3 +290,107 @@ def scale_channels(x, s, out_dtype, per_sample, C):
     check(lib().ld_scale_channels(_p(x), c_int(dt(x)), _p(s), _p(y), c_int(dt(y)), c_int64(x.numel()), c_int64(per_sample),
                                   c_int(C), _stream()), "ld_scale_channels")
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution support (channels-last bf16)
+def conv_out_size(n, k, stride, pad):
+    return (n + 2 * pad - k) // stride + 1
+
+
+def im2col(x, B, H, W, C, KH, KW, stride, pad):
+    """x: bf16 NHWC (any shape with B*H*W*C elements, contiguous) -> cols bf16 [B*Ho*Wo, pad8(KH*KW*C)]."""
+    _cuda(x)
+    Ho, Wo = conv_out_size(H, KH, stride, pad), conv_out_size(W, KW, stride, pad)
+    Kp = (KH * KW * C + 7) // 8 * 8
+    cols = torch.empty((B * Ho * Wo, Kp), dtype=torch.bfloat16, device=x.device)
+    check(lib().ld_im2col_nhwc(_p(x), _p(cols), c_int(B), c_int(H), c_int(W), c_int(C), c_int(Ho), c_int(Wo),
+                               c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(Kp), _stream()), "ld_im2col_nhwc")
+    return cols, Ho, Wo
+
+
+def col2im(cols, B, H, W, C, Ho, Wo, KH, KW, stride, pad):
+    """Gather-form inverse of im2col: cols [B*Ho*Wo, Kp] -> bf16 [B*H*W, C]."""
+    _cuda(cols)
+    out = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=cols.device)
+    check(lib().ld_col2im_nhwc(_p(cols), _p(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(Ho), c_int(Wo),
+                               c_int(KH), c_int(KW), c_int(stride), c_int(pad), c_int(cols.stride(0)), _stream()),
+          "ld_col2im_nhwc")
+    return out
+
+
+def maxpool3s2_fwd(x, B, H, W, C, save_argmax):
+    Ho, Wo = conv_out_size(H, 3, 2, 1), conv_out_size(W, 3, 2, 1)
+    y = torch.empty((B * Ho * Wo, C), dtype=torch.bfloat16, device=x.device)
+    arg = torch.empty((B * Ho * Wo, C), dtype=torch.uint8, device=x.device) if save_argmax else None
+    check(lib().ld_maxpool3s2_fwd(_p(x), _p(y), _p(arg), c_int(B), c_int(H), c_int(W), c_int(C), _stream()), "ld_maxpool3s2_fwd")
+    return y, arg, Ho, Wo
+
+
+def maxpool3s2_bwd(dy, arg, B, H, W, C):
+    dx = torch.empty((B * H * W, C), dtype=torch.bfloat16, device=dy.device)
+    check(lib().ld_maxpool3s2_bwd(_p(dy), _p(arg), _p(dx), c_int(B), c_int(H), c_int(W), c_int(C), _stream()), "ld_maxpool3s2_bwd")
+    return dx
+
+
+def nchw_to_nhwc(x, out_dtype):
+    """[B, C, H, W] contiguous -> [B*H*W, C] contiguous (dtype conversion fused)."""
+    _cuda(x)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    out = torch.empty((B * H * W, C), dtype=out_dtype, device=x.device)
+    check(lib().ld_layout_convert(_p(x), c_int(dt(x)), _p(out), c_int(dt(out)), c_int(B), c_int(C), c_int64(H * W), c_int(0),
+                                  _stream()), "ld_layout_convert")
+    return out
+
+
+def nhwc_to_nchw(x, B, C, H, W, out_dtype):
+    """[B*H*W, C] contiguous -> [B, C, H, W] contiguous."""
+    _cuda(x)
+    x = x.contiguous()
+    out = torch.empty((B, C, H, W), dtype=out_dtype, device=x.device)
+    check(lib().ld_layout_convert(_p(x), c_int(dt(x)), _p(out), c_int(dt(out)), c_int(B), c_int(C), c_int64(H * W), c_int(1),
+                                  _stream()), "ld_layout_convert")
+    return out
+
+
+def upfirdn2d_raw(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip_filter, gain, channels_last_out=None):
+    """x: 4-D [N, C, H, W] view with arbitrary strides (NCHW or channels-last), fp32 or bf16; f: fp32 [fh, fw]."""
+    _cuda(x, f)
+    assert x.ndim == 4 and f.ndim == 2 and f.dtype == torch.float32
+    f = f.contiguous()
+    N, C, H, W = x.shape
+    fh, fw = f.shape
+    outH = (H * upy + pady0 + pady1 - fh + downy) // downy
+    outW = (W * upx + padx0 + padx1 - fw + downx) // downx
+    cl = (x.stride(1) == 1 and C > 1) if channels_last_out is None else channels_last_out
+    y = torch.empty((N, C, outH, outW), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last if cl else torch.contiguous_format)
+    xs = (c_int64 * 4)(*x.stride())
+    ys = (c_int64 * 4)(*y.stride())
+    check(lib().ld_upfirdn2d(_p(x), _p(y), c_int(dt(x)), _p(f), c_int(fh), c_int(fw), c_int(N), c_int(C), c_int(H), c_int(W),
+                             c_int(outH), c_int(outW), xs, ys, c_int(upx), c_int(upy), c_int(downx), c_int(downy),
+                             c_int(padx0), c_int(padx1), c_int(pady0), c_int(pady1), c_int(1 if flip_filter else 0),
+                             c_float(gain), _stream()), "ld_upfirdn2d")
+    return y
+
+
+def demod_bias_act_fwd(x, d, bias, B, pixels, C, act, gain):
+    y = torch.empty((B * pixels, C), dtype=torch.bfloat16, device=x.device)
+    check(lib().ld_demod_bias_act_fwd(_p(x), c_int(dt(x)), _p(d), _p(bias), _p(y), c_int(B), c_int64(pixels), c_int(C),
+                                      c_int(act), c_float(gain), _stream()), "ld_demod_bias_act_fwd")
+    return y
+
+
+def demod_bias_act_bwd(dy, y, x, d, dd, dbias, B, pixels, C, act, gain):
+    dx = torch.empty((B * pixels, C), dtype=torch.bfloat16, device=x.device)
+    check(lib().ld_demod_bias_act_bwd(_p(dy), _p(y), _p(x), c_int(dt(x)), _p(d), _p(dx), _p(dd), _p(dbias), c_int(B),
+                                      c_int64(pixels), c_int(C), c_int(act), c_float(gain), _stream()), "ld_demod_bias_act_bwd")
+    return dx
+
+
+def channel_dot(a, g, B, pixels, C):
+    out = torch.zeros((B, C), dtype=torch.float32, device=a.device)
+    check(lib().ld_channel_dot(_p(a), c_int(dt(a)), _p(g), _p(out), c_int(B), c_int64(pixels), c_int(C), _stream()),
+          "ld_channel_dot")
+    return out

@@ -1,0 +1,278 @@
+"""BLIP "MED" BERT text encoder / causal LM decoder on the sm_100a kernels.
+
+Mirror of the reference's training/med.py for the code path LayoutDETR actually takes
+(`mode='text'`: self-attention only, cross-attention parameters exist but are never used,
+training/med.py:361).  Module / parameter names reproduce the reference state_dict tree
+(`embeddings.word_embeddings.weight`, `encoder.layer.{i}.attention.self.query.weight`, ...,
+`cls.predictions.decoder.weight` tied to the word embeddings) so checkpoints load by name.
+
+Dropout (hidden 0.1 / attention 0.1 in configs/med_config.json) is not applied: the kernels
+implement the deterministic (eval / p=0) semantics the parity contract is stated in.
+"""
+import json
+import math
+import types
+
+import torch
+import torch.nn as nn
+
+from .. import functional as Fn
+from .. import kernels as K
+
+
+class BertConfig:
+    """Plain-attribute stand-in for transformers.BertConfig (reference training/med.py:27)."""
+
+    def __init__(self, **kw):
+        self.vocab_size = 30522
+        self.hidden_size = 768
+        self.num_hidden_layers = 12
+        self.num_attention_heads = 12
+        self.intermediate_size = 3072
+        self.hidden_act = "gelu"
+        self.hidden_dropout_prob = 0.1
+        self.attention_probs_dropout_prob = 0.1
+        self.max_position_embeddings = 512
+        self.layer_norm_eps = 1e-12
+        self.pad_token_id = 0
+        self.initializer_range = 0.02
+        self.encoder_width = 768
+        self.add_cross_attention = True
+        self.__dict__.update(kw)
+
+    @classmethod
+    def from_json_file(cls, path):
+        with open(path) as f:
+            return cls(**json.load(f))
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+
+class BertEmbeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
+        self.eps = config.layer_norm_eps
+        self.pad_token_id = config.pad_token_id
+
+    def forward(self, input_ids):
+        B, T = input_ids.shape
+        return Fn.EmbedLNFn.apply(input_ids.contiguous(), self.word_embeddings.weight, self.position_embeddings.weight,
+                                  self.LayerNorm.weight, self.LayerNorm.bias, T, self.eps, self.pad_token_id)
+
+
+class BertSelfAttention(nn.Module):
+    def __init__(self, config, is_cross_attention):
+        super().__init__()
+        kv_in = config.encoder_width if is_cross_attention else config.hidden_size
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = config.hidden_size // config.num_attention_heads
+        self.query = nn.Linear(config.hidden_size, config.hidden_size)
+        self.key = nn.Linear(kv_in, config.hidden_size)
+        self.value = nn.Linear(kv_in, config.hidden_size)
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config, is_cross_attention=False):
+        super().__init__()
+        self.self = BertSelfAttention(config, is_cross_attention)
+        self.output = BertSelfOutput(config)
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+
+
+class BertOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, config, layer_num):
+        super().__init__()
+        self.attention = BertAttention(config)
+        self.layer_num = layer_num
+        if config.add_cross_attention:
+            self.crossattention = BertAttention(config, is_cross_attention=True)   # parameters only (mode='text')
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+        self.eps = config.layer_norm_eps
+
+    def forward(self, x, B, T, key_mask, causal):
+        """x: bf16 [B*T, hidden].  Post-norm BERT layer (reference training/med.py:336-386)."""
+        sa = self.attention.self
+        H, d = sa.num_attention_heads, sa.attention_head_size
+        qkv = Fn.fused_linear(x, (sa.query, sa.key, sa.value))
+        ctx = Fn.attention(qkv, qkv, qkv, 0, H * d, 2 * H * d, B, H, T, T, d, 1.0 / math.sqrt(d),
+                           key_mask=key_mask, mask_inf=False, causal=causal)
+        so = self.attention.output
+        h = Fn.linear_ln(ctx, x, so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias, self.eps)
+        inter = Fn.linear(h, self.intermediate.dense.weight, self.intermediate.dense.bias, act=K.ACT_GELU)
+        o = self.output
+        return Fn.linear_ln(inter, h, o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias, self.eps)
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
+
+
+def _init_bert_weights(module, std):
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        module.weight.data.normal_(mean=0.0, std=std)
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+    if isinstance(module, nn.Linear) and module.bias is not None:
+        module.bias.data.zero_()
+
+
+class BertModel(nn.Module):
+    """Text encoder (`add_pooling_layer=False`).  forward(...) keeps the reference call form
+    `text_encoder(input_ids, attention_mask=..., return_dict=True, mode='text')`."""
+
+    def __init__(self, config, add_pooling_layer=False):
+        super().__init__()
+        assert not add_pooling_layer
+        self.config = config
+        self.embeddings = BertEmbeddings(config)
+        self.encoder = BertEncoder(config)
+        self.apply(lambda m: _init_bert_weights(m, config.initializer_range))
+
+    @classmethod
+    def from_pretrained(cls, name, config=None, **kw):
+        # no network / no checkpoint files on the build and GPU boxes: random init, weights arrive by state_dict
+        return cls(config, **kw)
+
+    def resize_token_embeddings(self, n):
+        old = self.embeddings.word_embeddings
+        if n == old.num_embeddings:
+            return old
+        new = nn.Embedding(n, old.embedding_dim, padding_idx=old.padding_idx)
+        new.weight.data.normal_(0.0, self.config.initializer_range)
+        k = min(n, old.num_embeddings)
+        new.weight.data[:k] = old.weight.data[:k]
+        self.embeddings.word_embeddings = new
+        self.config.vocab_size = n
+        return new
+
+    def hidden_states(self, input_ids, attention_mask, causal=False):
+        """-> bf16 [B*T, hidden] last-layer hidden states."""
+        B, T = input_ids.shape
+        key_mask = (attention_mask == 0).to(torch.uint8).contiguous()
+        x = self.embeddings(input_ids)
+        for layer in self.encoder.layer:
+            x = layer(x, B, T, key_mask, causal)
+        return x
+
+    def forward(self, input_ids, attention_mask=None, return_dict=True, mode="text", is_decoder=False, **_):
+        if mode != "text":
+            raise NotImplementedError("only mode='text' is on the LayoutDETR path (training/networks_detr.py:146)")
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        B, T = input_ids.shape
+        x = self.hidden_states(input_ids, attention_mask, causal=is_decoder)
+        return types.SimpleNamespace(last_hidden_state=Fn.to_f32(x).view(B, T, -1))
+
+    def cls_features(self, input_ids, attention_mask):
+        """-> bf16 [B, hidden]: last_hidden_state[:, 0, :] (the only part of the encoder output LayoutDETR reads)."""
+        B, T = input_ids.shape
+        x = self.hidden_states(input_ids, attention_mask)
+        return x.view(B, T, -1)[:, 0, :]
+
+
+class BertPredictionHeadTransform(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class BertLMPredictionHead(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        self.decoder = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.bias = nn.Parameter(torch.zeros(config.vocab_size))
+        self.decoder.bias = self.bias
+
+
+class BertOnlyMLMHead(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.predictions = BertLMPredictionHead(config)
+
+
+class BertLMHeadModel(nn.Module):
+    """Causal LM text decoder; forward(...) returns an object with `.loss` (label-smoothed next-token CE,
+    reference training/med.py:833-933)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.bert = BertModel(config, add_pooling_layer=False)
+        self.cls = BertOnlyMLMHead(config)
+        self.apply(lambda m: _init_bert_weights(m, config.initializer_range))
+        self._tie()
+
+    def _tie(self):
+        self.cls.predictions.decoder.weight = self.bert.embeddings.word_embeddings.weight
+
+    @classmethod
+    def from_pretrained(cls, name, config=None, **kw):
+        return cls(config, **kw)
+
+    def resize_token_embeddings(self, n):
+        old_n = self.bert.embeddings.word_embeddings.num_embeddings
+        new = self.bert.resize_token_embeddings(n)
+        self.config.vocab_size = n
+        pred = self.cls.predictions
+        if n != old_n:
+            dec = nn.Linear(new.embedding_dim, n, bias=False)
+            bias = nn.Parameter(torch.zeros(n))
+            k = min(n, old_n)
+            bias.data[:k] = pred.bias.data[:k]
+            pred.bias = bias
+            dec.bias = bias
+            pred.decoder = dec
+        self._tie()
+        return new
+
+    def forward(self, input_ids, attention_mask=None, labels=None, return_dict=True, mode="text", n_valid=None, **_):
+        if mode != "text":
+            raise NotImplementedError("only mode='text' is on the LayoutDETR path (training/networks_detr.py:180,339)")
+        B, T = input_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        x = self.bert.hidden_states(input_ids, attention_mask, causal=True)
+        tr = self.cls.predictions.transform
+        h = Fn.linear(x, tr.dense.weight, tr.dense.bias, act=K.ACT_GELU)
+        h = Fn.layernorm(h, tr.LayerNorm.weight, tr.LayerNorm.bias, self.config.layer_norm_eps)
+        if labels is None:
+            raise NotImplementedError("logits-only decoding is not on the training path")
+        # next-token prediction: position t predicts labels[t+1]; the last position has no target
+        shifted = torch.full_like(labels, -100)
+        shifted[:, :-1] = labels[:, 1:]
+        if n_valid is None:
+            n_valid = int((shifted != -100).sum())
+        loss = Fn.lm_head_ce(h, self.bert.embeddings.word_embeddings.weight, self.cls.predictions.bias,
+                             shifted.reshape(-1).contiguous(), n_valid, 0.1)
+        return types.SimpleNamespace(loss=loss)

@@ -1,0 +1,405 @@
+"""LayoutDETR Generator / Discriminator on the sm_100a kernels — drop-in mirror of the reference's
+training/networks_detr.py (Generator :65-187, Discriminator :190-361): same constructor signatures,
+forward signatures / return tuples, attribute names and state_dict keys, so `training_loop`, the
+metrics and `generate.py` can use these classes unchanged and reference checkpoints load by name.
+
+All heavy math (ResNet-50 convs, BERT encoder/decoder, DETR attention + FFN, LM head + loss,
+StyleGAN2 background decoder) runs in hand-written CUDA through layoutdetr_b200.functional; PyTorch
+ops appear only as glue on tiny tensors (concatenation / indexing of `[B*9, d]` rows, scalar losses).
+There is no CPU path: inputs must live on a CUDA device.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as Fn
+from .. import kernels as K
+from .detr_backbone import build_backbone as _build_backbone
+from .detr_transformer import Transformer, TransformerWithToken, TransformerEncoderStack
+from .med import BertConfig, BertModel, BertLMHeadModel
+from .util import TransformerWithToken_layoutganpp
+
+
+def merge_lists(lists):
+    ret = []
+    for l in lists:
+        ret += l
+    return ret
+
+
+def split_list(list_a, chunk_size):
+    return [list_a[i:i + chunk_size] for i in range(0, len(list_a), chunk_size)]
+
+
+def normalize_2nd_moment(x, eps=1e-8):
+    return x * (x.square().mean(dim=1, keepdim=True) + eps).rsqrt()
+
+
+def build_backbone():
+    return _build_backbone()
+
+
+def init_tokenizer():
+    """BertTokenizer('bert-base-uncased') + [DEC]/[ENC] when a local vocab exists (reference training/blip.py:190),
+    otherwise the deterministic synthetic tokenizer with the same special-token layout."""
+    try:
+        if os.environ.get("LAYOUTDETR_SYNTHETIC_TOKENIZER", "0") != "1":
+            from transformers import BertTokenizer
+            tok = BertTokenizer.from_pretrained("bert-base-uncased", local_files_only=True)
+            tok.add_special_tokens({"bos_token": "[DEC]"})
+            tok.add_special_tokens({"additional_special_tokens": ["[ENC]"]})
+            tok.enc_token_id = tok.additional_special_tokens_ids[0]
+            return tok
+    except Exception:
+        pass
+    from ..synthetic import SyntheticTokenizer
+    return SyntheticTokenizer()
+
+
+def _med_config(path):
+    if path is not None and os.path.exists(path):
+        return BertConfig.from_json_file(path)
+    return BertConfig.default()       # identical to the reference's configs/med_config.json
+
+
+class MLP(nn.Module):
+    """Linear/ReLU stack (reference training/networks_detr.py:50-62); `final_act` fuses the caller's
+    trailing `torch.relu(...)` into the last GEMM epilogue."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+    def forward(self, x, final_act=K.ACT_NONE, out_f32=False):
+        for i, layer in enumerate(self.layers):
+            last = i == self.num_layers - 1
+            if last and out_f32:
+                x = Fn.linear_f32(x, layer.weight, layer.bias)
+            else:
+                x = Fn.linear(x, layer.weight, layer.bias, act=final_act if last else K.ACT_RELU)
+        return x
+
+
+class _TextFrontEnd:
+    """Host-side text handling shared by G and D: tokenise once per distinct batch of strings, keep the
+    device copies, and remember the host-side facts (valid slots, token counts) so the forward pass never
+    synchronises on the device to learn a shape."""
+
+    def __init__(self, tokenizer, max_text_length):
+        self.tokenizer = tokenizer
+        self.max_text_length = max_text_length
+        self._key = None
+        self._val = None
+
+    def __call__(self, bbox_text, device):
+        flat = merge_lists(bbox_text)
+        key = (tuple(flat), str(device))
+        if key != self._key:
+            enc = self.tokenizer(flat, padding="max_length", truncation=True, max_length=self.max_text_length,
+                                 return_tensors="pt")
+            ids, mask = enc.input_ids, enc.attention_mask
+            text_len = torch.from_numpy(np.array([len(t) for t in flat], dtype=np.int64))
+            self._val = dict(ids=ids.to(device), mask=mask.to(device), ids_cpu=ids, mask_cpu=mask,
+                             text_len=text_len.to(device))
+            self._key = key
+        return self._val
+
+
+_host_mask_cache = {}
+
+
+def _host_mask(padding_mask):
+    """CPU copy of the (tiny) padding mask, cached per tensor version: one D2H sync per new batch."""
+    key = (padding_mask.data_ptr(), padding_mask._version, tuple(padding_mask.shape))
+    v = _host_mask_cache.get(key)
+    if v is None:
+        if len(_host_mask_cache) > 16:
+            _host_mask_cache.clear()
+        v = padding_mask.detach().cpu().numpy().astype(bool)
+        _host_mask_cache[key] = v
+    return v
+
+
+def _encode_text(module, text, B, N):
+    """CLS feature of the frozen/unfrozen text encoder for every slot -> bf16 [B*N, bert_f_dim]."""
+    enc = module.text_encoder
+    ids, mask = text["ids"], text["mask"]
+    if module.text_trim:
+        T = int(text["mask_cpu"].sum(1).max())
+        T = min(ids.shape[1], (T + 7) // 8 * 8)
+        ids, mask = ids[:, :T].contiguous(), mask[:, :T].contiguous()
+    frozen = not any(p.requires_grad for p in enc.parameters())
+    if module.text_dedup and frozen:
+        key = (id(text["ids"]), ids.shape[1], tuple(p._version for p in enc.parameters()))
+        if module._cls_cache is not None and module._cls_cache[0] == key:
+            return module._cls_cache[1]
+        with torch.no_grad():
+            feat = enc.cls_features(ids, mask).contiguous()
+        module._cls_cache = (key, feat)
+        return feat
+    return enc.cls_features(ids, mask).contiguous()
+
+
+def _decode_text_loss(module, text, valid_idx_dev, valid_idx_cpu, bos_id, pad_id):
+    """Causal-LM reconstruction loss of the strings of the valid slots (reference :169-181 / :328-340).
+    The decoder runs mode='text': `encoder_hidden_states` is never read (training/med.py:361)."""
+    ids = text["ids"].index_select(0, valid_idx_dev).clone()
+    mask = text["mask"].index_select(0, valid_idx_dev)
+    mask_cpu = text["mask_cpu"][valid_idx_cpu]
+    if module.text_trim:
+        T = int(mask_cpu.sum(1).max())
+        T = min(ids.shape[1], (T + 7) // 8 * 8)
+        ids, mask, mask_cpu = ids[:, :T].contiguous(), mask[:, :T].contiguous(), mask_cpu[:, :T]
+    ids[:, 0] = bos_id
+    labels = ids.masked_fill(ids == pad_id, -100)
+    # next-token targets: positions 1.. of every non-pad token
+    ids_cpu = text["ids_cpu"][valid_idx_cpu][:, :ids.shape[1]]
+    n_valid = int(((ids_cpu != pad_id)[:, 1:]).sum())
+    out = module.text_decoder(ids, attention_mask=mask, labels=labels, return_dict=True, mode="text", n_valid=n_valid)
+    return out.loss
+
+
+class Generator(nn.Module):
+    def __init__(self, z_dim, num_bbox_labels, img_channels, img_height, img_width, c_dim,
+                 f_dim=256, num_heads=4, num_layers=8,
+                 hidden_dim=256,
+                 med_config='configs/med_config.json', bert_f_dim=768, bert_num_encoder_layers=12, bert_num_decoder_layers=12, bert_num_heads=12,
+                 background_size=1024, im_f_dim=512,
+                 max_text_length=256):
+        super().__init__()
+        self.z_dim = z_dim
+        self.num_bbox_labels = num_bbox_labels
+        self.c_dim = c_dim
+        self.max_text_length = max_text_length
+        self.hidden_dim = hidden_dim
+        # execution options (exact, parity-preserving): see DESIGN.md "text path"
+        self.text_trim = False       # drop all-padding token columns before the BERT stacks
+        self.text_dedup = False      # reuse the frozen encoder's CLS features across calls on the same strings
+        self._cls_cache = None
+
+        self.backbone = build_backbone()
+        self.input_proj = nn.Conv2d(self.backbone.num_channels, hidden_dim, kernel_size=1)
+
+        self.fc_z = nn.Linear(z_dim * 9, bert_f_dim)
+        self.emb_label = nn.Embedding(num_bbox_labels, bert_f_dim)
+
+        self.tokenizer = init_tokenizer()
+        encoder_config = _med_config(med_config)
+        encoder_config.encoder_width = bert_f_dim
+        encoder_config.num_hidden_layers = bert_num_encoder_layers
+        encoder_config.num_attention_heads = bert_num_heads
+        self.text_encoder = BertModel.from_pretrained('bert-base-uncased', config=encoder_config, add_pooling_layer=False)
+        self.text_encoder.resize_token_embeddings(len(self.tokenizer))
+
+        self.enc_text_len = nn.Embedding(max_text_length, bert_f_dim)
+        self.fc_in = MLP(input_dim=bert_f_dim * 4, hidden_dim=bert_f_dim, output_dim=hidden_dim, num_layers=3)
+
+        self.transformer = Transformer(d_model=hidden_dim, dropout=0.1, nhead=8, dim_feedforward=2048,
+                                       num_encoder_layers=6, num_decoder_layers=6, normalize_before=False,
+                                       return_intermediate_dec=False)
+        self.bbox_embed = MLP(input_dim=hidden_dim, hidden_dim=hidden_dim, output_dim=4, num_layers=3)
+
+        self.fc_z_rec = nn.Linear(hidden_dim, z_dim * 9)
+        self.fc_out_cls = nn.Linear(hidden_dim, num_bbox_labels)
+
+        decoder_config = _med_config(med_config)
+        decoder_config.encoder_width = im_f_dim
+        decoder_config.num_hidden_layers = bert_num_decoder_layers
+        decoder_config.num_attention_heads = bert_num_heads
+        self.text_decoder = BertLMHeadModel.from_pretrained('bert-base-uncased', config=decoder_config)
+        self.text_decoder.resize_token_embeddings(len(self.tokenizer))
+
+        self.fc_text_len_rec = nn.Linear(hidden_dim, max_text_length)
+        self._text = None
+
+    def _front(self):
+        if self._text is None or self._text.tokenizer is not self.tokenizer:
+            self._text = _TextFrontEnd(self.tokenizer, self.max_text_length)
+        return self._text
+
+    def forward(self, z, bbox_class, bbox_real, bbox_text, bbox_patch, padding_mask, background, c, reconst=False):
+        if isinstance(background, (list, tuple)):
+            background = torch.stack(list(background))
+        dev = background.device
+        if dev.type != "cuda":
+            raise RuntimeError("layoutdetr_b200.Generator runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, N = bbox_patch.shape[0], bbox_patch.shape[1]
+        H = self.hidden_dim
+
+        feat, pos, h, w = self.backbone(background.float())
+        S = h * w
+        src = Fn.conv2d(feat, self.input_proj.weight, None, self.input_proj.bias, None, B, h, w, 1, 0, K.ACT_NONE)
+
+        z0 = normalize_2nd_moment(z.reshape(B, -1).float())
+        zf = Fn.linear(Fn.to_bf16_padded(z0), self.fc_z.weight, self.fc_z.bias)                     # [B, 768]
+        l = F.embedding(bbox_class, self.emb_label.weight)                                          # [B, N, 768]
+        text = self._front()(bbox_text, dev)
+        text_feat = _encode_text(self, text, B, N)                                                  # [B*N, 768] bf16
+        text_len = text["text_len"].view(B, N)
+        text_len_feat = F.embedding(text_len, self.enc_text_len.weight)
+        x = torch.cat([zf.unsqueeze(1).expand(-1, N, -1), l.to(torch.bfloat16), text_feat.view(B, N, -1),
+                       text_len_feat.to(torch.bfloat16)], dim=-1).reshape(B * N, -1)
+        x = self.fc_in(x, final_act=K.ACT_RELU)                                                     # [B*N, 256]
+
+        hs, _, _ = self.transformer(src, pos, x, padding_mask, B, S, N)                             # [B*N, 256]
+        bbox_fake = self.bbox_embed(hs, out_f32=True).sigmoid().view(B, N, 4)
+        if not reconst:
+            return bbox_fake
+
+        valid_cpu = np.flatnonzero(~_host_mask(padding_mask).reshape(-1))
+        valid = torch.from_numpy(valid_cpu).to(dev)
+        xv = hs.index_select(0, valid)                                                              # [M, 256]
+        z_rec = Fn.linear_f32(xv, self.fc_z_rec.weight, self.fc_z_rec.bias)
+        z_tgt = z0.unsqueeze(1).expand(-1, N, -1).reshape(B * N, -1).index_select(0, valid)
+        loss_z = F.mse_loss(z_rec, z_tgt)
+        logit_cls = Fn.linear_f32(xv, self.fc_out_cls.weight, self.fc_out_cls.bias)
+        loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+        text_len_rec = Fn.linear_f32(xv, self.fc_text_len_rec.weight, self.fc_text_len_rec.bias)
+        loss_text_len = Fn.cross_entropy(text_len_rec, text_len.reshape(-1).index_select(0, valid))
+        return bbox_fake, loss_z, logit_cls, loss_lm, loss_text_len
+
+
+class Discriminator(nn.Module):
+    def __init__(self, num_bbox_labels, img_channels, img_height, img_width, c_dim,
+                 f_dim=256, num_heads=4, num_layers=8, max_bbox=50,
+                 hidden_dim=256,
+                 med_config='configs/med_config.json', bert_f_dim=768, bert_num_encoder_layers=12, bert_num_decoder_layers=12, bert_num_heads=12,
+                 background_size=1024, im_f_dim=512,
+                 max_text_length=256):
+        super().__init__()
+        from .networks_stylegan2 import Decoder
+        self.num_bbox_labels = num_bbox_labels
+        self.c_dim = c_dim
+        self.max_text_length = max_text_length
+        self.hidden_dim = hidden_dim
+        self.text_trim = False
+        self.text_dedup = False
+        self._cls_cache = None
+
+        self.backbone = build_backbone()
+        self.input_proj = nn.Conv2d(self.backbone.num_channels, hidden_dim, kernel_size=1)
+
+        self.fc_bbox = nn.Linear(4, bert_f_dim)
+        self.emb_label = nn.Embedding(num_bbox_labels, bert_f_dim)
+
+        self.tokenizer = init_tokenizer()
+        encoder_config = _med_config(med_config)
+        encoder_config.encoder_width = bert_f_dim
+        encoder_config.num_hidden_layers = bert_num_encoder_layers
+        encoder_config.num_attention_heads = bert_num_heads
+        self.text_encoder = BertModel.from_pretrained('bert-base-uncased', config=encoder_config, add_pooling_layer=False)
+        self.text_encoder.resize_token_embeddings(len(self.tokenizer))
+
+        self.enc_text_len = nn.Embedding(max_text_length, bert_f_dim)
+        self.enc_fc_in = MLP(input_dim=bert_f_dim * 4, hidden_dim=bert_f_dim, output_dim=hidden_dim, num_layers=3)
+        self.enc_transformer = TransformerWithToken(d_model=hidden_dim, dropout=0.1, nhead=8, dim_feedforward=2048,
+                                                    num_encoder_layers=6, num_decoder_layers=6, normalize_before=False,
+                                                    return_intermediate_dec=False)
+        self.fc_out_disc = nn.Linear(hidden_dim, 1)
+
+        self.pos_token = nn.Parameter(torch.rand(max_bbox, 1, hidden_dim))
+        self.dec_fc_in = nn.Linear(hidden_dim + hidden_dim, hidden_dim)
+        te = nn.TransformerEncoderLayer(d_model=hidden_dim, nhead=8, dim_feedforward=2048)
+        self.dec_transformer = nn.TransformerEncoder(te, num_layers=6, enable_nested_tensor=False)
+        self.bbox_embed = nn.Linear(hidden_dim, 4)
+        self.fc_out_cls = nn.Linear(hidden_dim, num_bbox_labels)
+
+        decoder_config = _med_config(med_config)
+        decoder_config.encoder_width = im_f_dim
+        decoder_config.num_hidden_layers = bert_num_decoder_layers
+        decoder_config.num_attention_heads = bert_num_heads
+        self.text_decoder = BertLMHeadModel.from_pretrained('bert-base-uncased', config=decoder_config)
+        self.text_decoder.resize_token_embeddings(len(self.tokenizer))
+
+        self.fc_text_len_rec = nn.Linear(hidden_dim, max_text_length)
+        self.bg_decoder = Decoder(z_dim=hidden_dim, w_dim=im_f_dim, channel_max=im_f_dim, channel_base=8192,
+                                  img_channels=img_channels, img_resolution=background_size, use_noise=False,
+                                  num_fp16_res=0, conv_clamp=None, fused_modconv_default=False)
+
+        self.fc_bbox_uncond = nn.Linear(4, bert_f_dim)
+        self.emb_label_uncond = nn.Embedding(num_bbox_labels, bert_f_dim)
+        self.enc_fc_in_uncond = MLP(input_dim=bert_f_dim + bert_f_dim, hidden_dim=bert_f_dim, output_dim=hidden_dim, num_layers=3)
+        self.enc_transformer_uncond = TransformerWithToken_layoutganpp(d_model=hidden_dim, dim_feedforward=2048, nhead=8, num_layers=6)
+        self.fc_out_disc_uncond = nn.Linear(hidden_dim, 1)
+
+        self.pos_token_uncond = nn.Parameter(torch.rand(max_bbox, 1, hidden_dim))
+        self.dec_fc_in_uncond = nn.Linear(hidden_dim + hidden_dim, hidden_dim)
+        te_uncond = nn.TransformerEncoderLayer(d_model=hidden_dim, nhead=8, dim_feedforward=2048)
+        self.dec_transformer_uncond = nn.TransformerEncoder(te_uncond, num_layers=6, enable_nested_tensor=False)
+        self.bbox_embed_uncond = nn.Linear(hidden_dim, 4)
+        self.fc_out_cls_uncond = nn.Linear(hidden_dim, num_bbox_labels)
+        self._text = None
+
+    def _front(self):
+        if self._text is None or self._text.tokenizer is not self.tokenizer:
+            self._text = _TextFrontEnd(self.tokenizer, self.max_text_length)
+        return self._text
+
+    def _decode_branch(self, x0, pos_token, dec_fc_in, dec_transformer, B, N, padding_mask, valid):
+        """x0 [B, H] bf16 -> per-slot features of the valid slots [M, H] (reference :315-321, :352-357)."""
+        H = self.hidden_dim
+        t = Fn.to_bf16_padded(pos_token[:N].reshape(N, H))                                          # [N, H]
+        x = torch.cat([x0.unsqueeze(1).expand(-1, N, -1), t.unsqueeze(0).expand(B, -1, -1)], dim=-1).reshape(B * N, 2 * H)
+        x = Fn.linear(x, dec_fc_in.weight, dec_fc_in.bias, act=K.ACT_RELU)
+        x = TransformerEncoderStack.run(dec_transformer, x, B, N, padding_mask)
+        return x.index_select(0, valid)
+
+    def forward(self, bbox, bbox_class, bbox_text, bbox_patch, padding_mask, background, c, reconst=False):
+        if isinstance(background, (list, tuple)):
+            background = torch.stack(list(background))
+        dev = background.device
+        if dev.type != "cuda":
+            raise RuntimeError("layoutdetr_b200.Discriminator runs on CUDA (sm_100a) only; there is no CPU fallback")
+        B, N = bbox_patch.shape[0], bbox_patch.shape[1]
+        H = self.hidden_dim
+
+        feat, pos, h, w = self.backbone(background.float())
+        S = h * w
+        src = Fn.conv2d(feat, self.input_proj.weight, None, self.input_proj.bias, None, B, h, w, 1, 0, K.ACT_NONE)
+
+        bbox2d = Fn.to_bf16_padded(bbox.reshape(B * N, 4).float())
+        b = Fn.linear(bbox2d, self.fc_bbox.weight, self.fc_bbox.bias)                               # [B*N, 768]
+        l = F.embedding(bbox_class, self.emb_label.weight)
+        text = self._front()(bbox_text, dev)
+        text_feat = _encode_text(self, text, B, N)
+        text_len = text["text_len"].view(B, N)
+        text_len_feat = F.embedding(text_len, self.enc_text_len.weight)
+        x = torch.cat([b.view(B, N, -1), l.to(torch.bfloat16), text_feat.view(B, N, -1),
+                       text_len_feat.to(torch.bfloat16)], dim=-1).reshape(B * N, -1)
+        x = self.enc_fc_in(x, final_act=K.ACT_RELU)
+
+        hs, _, L = self.enc_transformer(src, pos, x, padding_mask, B, S, N)                         # [B*(N+1), 256]
+        x0 = hs.view(B, L, H)[:, 0, :]                                                              # token output
+        logit_disc = Fn.linear_f32(x0, self.fc_out_disc.weight, self.fc_out_disc.bias).squeeze(-1)
+
+        b_u = Fn.linear(bbox2d, self.fc_bbox_uncond.weight, self.fc_bbox_uncond.bias)
+        l_u = F.embedding(bbox_class, self.emb_label_uncond.weight)
+        x_u = torch.cat([b_u.view(B, N, -1), l_u.to(torch.bfloat16)], dim=-1).reshape(B * N, -1)
+        x_u = self.enc_fc_in_uncond(x_u, final_act=K.ACT_RELU)
+        x_u = self.enc_transformer_uncond(x_u, B, N, padding_mask)                                  # [B*(N+1), 256]
+        x0_u = x_u.view(B, N + 1, H)[:, 0, :]
+        logit_disc_uncond = Fn.linear_f32(x0_u, self.fc_out_disc_uncond.weight, self.fc_out_disc_uncond.bias).squeeze(-1)
+        if not reconst:
+            return logit_disc, logit_disc_uncond
+
+        valid_cpu = np.flatnonzero(~_host_mask(padding_mask).reshape(-1))
+        valid = torch.from_numpy(valid_cpu).to(dev)
+        xv = self._decode_branch(x0, self.pos_token, self.dec_fc_in, self.dec_transformer, B, N, padding_mask, valid)
+        bbox_pred = Fn.linear_f32(xv, self.bbox_embed.weight, self.bbox_embed.bias).sigmoid()
+        logit_cls = Fn.linear_f32(xv, self.fc_out_cls.weight, self.fc_out_cls.bias)
+        loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+        text_len_rec = Fn.linear_f32(xv, self.fc_text_len_rec.weight, self.fc_text_len_rec.bias)
+        loss_text_len = Fn.cross_entropy(text_len_rec, text_len.reshape(-1).index_select(0, valid))
+        bg_rec = self.bg_decoder(x0)
+
+        xv_u = self._decode_branch(x0_u, self.pos_token_uncond, self.dec_fc_in_uncond, self.dec_transformer_uncond,
+                                   B, N, padding_mask, valid)
+        bbox_pred_uncond = Fn.linear_f32(xv_u, self.bbox_embed_uncond.weight, self.bbox_embed_uncond.bias).sigmoid()
+        logit_cls_uncond = Fn.linear_f32(xv_u, self.fc_out_cls_uncond.weight, self.fc_out_cls_uncond.bias)
+        return (logit_disc, logit_disc_uncond, bbox_pred, logit_cls, loss_lm, loss_text_len, bg_rec,
+                bbox_pred_uncond, logit_cls_uncond)

@@ -1,0 +1,69 @@
+"""CPU: pin the oracle restatement (oracle/layoutdetr_oracle.py) against outputs of the REAL reference
+(tests/golden/*.pt, produced by tools/gen_golden.py where /root/reference exists)."""
+import os
+
+import pytest
+import torch
+
+from helpers import build, golden, state_dict_f32, GOLD
+
+
+def _tok():
+    from layoutdetr_b200.synthetic import SyntheticTokenizer
+    return SyntheticTokenizer()
+
+
+def test_state_dict_tree_matches_reference_manifest():
+    import json
+    with open(os.path.join(GOLD, "state_dict_manifest.json")) as f:
+        man = json.load(f)
+    for which in ("G", "D"):
+        ours = {k: list(v.shape) for k, v in build(which).state_dict().items()}
+        assert ours == man[which], "state_dict of %s differs from the reference tree" % which
+
+
+def test_oracle_ops_match_reference_ref_impls():
+    from oracle import layoutdetr_oracle as O
+    ops = golden("ops_ref.pt")
+    for c in ops["bias_act"]:
+        y = O.bias_act(c["x"], c["b"], dim=c["dim"], act=c["act"], gain=c["gain"], clamp=c["clamp"])
+        torch.testing.assert_close(y, c["y"], atol=1e-6, rtol=1e-6)
+    for c in ops["upfirdn2d"]:
+        y = O.upfirdn2d(c["x"], c["f"], up=c["up"], down=c["down"], padding=tuple(c["padding"]), flip_filter=c["flip_filter"], gain=c["gain"])
+        torch.testing.assert_close(y, c["y"], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["model_b1_v4"])
+def test_oracle_generator_matches_reference(name):
+    from layoutdetr_b200.synthetic import make_inputs
+    from oracle import layoutdetr_oracle as O
+    g = golden(name + ".pt")
+    inp = make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"])
+    sd = state_dict_f32(build("G"))
+    with torch.no_grad():
+        out = O.generator_forward(sd, _tok(), inp["z"], inp["bbox_class"], inp["bbox_text"], inp["padding_mask"],
+                                  inp["background"], reconst=True)
+    for key, val in zip(["bbox_fake", "loss_z", "logit_cls", "loss_lm", "loss_text_len"], out[:5]):
+        torch.testing.assert_close(val, g["G"][key], atol=2e-4, rtol=2e-4, msg=lambda m: "%s: %s" % (key, m))
+    torch.testing.assert_close(out[5]["text_cls"], g["G_inter"]["text_cls"], atol=2e-4, rtol=2e-4)
+    torch.testing.assert_close(out[5]["hs"], g["G_inter"]["hs"], atol=5e-4, rtol=5e-4)
+
+
+@pytest.mark.parametrize("name", ["model_b1_v4"])
+def test_oracle_discriminator_matches_reference(name):
+    from layoutdetr_b200.synthetic import make_inputs
+    from oracle import layoutdetr_oracle as O
+    g = golden(name + ".pt")
+    inp = make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"])
+    sd = state_dict_f32(build("D"))
+    names = ["logit_disc", "logit_disc_uncond", "bbox_pred", "logit_cls", "loss_lm", "loss_text_len", "bg_rec",
+             "bbox_pred_uncond", "logit_cls_uncond"]
+    with torch.no_grad():
+        out = O.discriminator_forward(sd, _tok(), inp["bbox_real"], inp["bbox_class"], inp["bbox_text"], inp["padding_mask"],
+                                      inp["background"], reconst=True)
+    for key, val in zip(names, out):
+        if key == "bg_rec":
+            torch.testing.assert_close(val[:, :, ::8, ::8], g["D"]["bg_rec_sub"], atol=1e-3, rtol=1e-3)
+            assert abs(float(val.mean()) - g["D"]["bg_rec_mean"]) < 1e-3 * max(1.0, abs(g["D"]["bg_rec_std"]))
+        else:
+            torch.testing.assert_close(val, g["D"][key], atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))

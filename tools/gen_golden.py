@@ -1,0 +1,204 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (build container only).
+
+    python tools/gen_golden.py [--skip-loss]
+
+Imports /root/reference through oracle/ref_shim.py, overwrites every parameter/buffer with
+layoutdetr_b200.synthetic.synth_tensor(name, shape) (a pure function of the state_dict key), runs the
+reference on layoutdetr_b200.synthetic.make_inputs(...) in eval mode on CPU/fp32 and stores the (small)
+outputs.  The GPU box has no reference: tests rebuild the same weights and inputs from the same pure
+functions and compare against these files.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from layoutdetr_b200.synthetic import make_inputs, synth_state_dict  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _hook_outputs(module, store, name):
+    def hook(_m, _inp, out):
+        t = out[0] if isinstance(out, (tuple, list)) else out
+        if isinstance(t, dict):
+            t = list(t.values())[-1]
+        if hasattr(t, "last_hidden_state"):
+            t = t.last_hidden_state
+        store[name] = t.detach().clone()
+    return module.register_forward_hook(hook)
+
+
+def gen_ops():
+    """bias_act / upfirdn2d reference implementations (impl='ref') on small seeded tensors."""
+    from torch_utils.ops import bias_act, upfirdn2d
+    g = torch.Generator().manual_seed(123)
+    out = {"bias_act": [], "upfirdn2d": []}
+    for act in ["linear", "relu", "lrelu", "tanh", "sigmoid", "elu", "selu", "softplus", "swish"]:
+        for (shape, dim, gain, clamp) in [((3, 5, 7, 6), 1, None, None), ((4, 16), 1, 0.7, 0.5)]:
+            x = torch.randn(shape, generator=g) * 2
+            b = torch.randn(shape[dim], generator=g)
+            xr = x.clone().requires_grad_(True)
+            br = b.clone().requires_grad_(True)
+            y = bias_act.bias_act(xr, br, dim=dim, act=act, gain=gain, clamp=clamp, impl="ref")
+            dy = torch.randn(shape, generator=g)
+            dx, db = torch.autograd.grad(y, [xr, br], dy)
+            out["bias_act"].append(dict(act=act, dim=dim, gain=gain, clamp=clamp, x=x, b=b, y=y.detach(), dy=dy, dx=dx, db=db))
+    f4 = upfirdn2d.setup_filter([1, 3, 3, 1])
+    f3 = upfirdn2d.setup_filter([1, 2, 1])
+    fsep = torch.tensor([0.25, 0.5, 0.25, 0.1, 0.3])
+    f2d = fsep.ger(fsep)
+    cases = [
+        dict(f=f4, up=1, down=1, padding=[1, 1, 1, 1], flip_filter=False, gain=4.0, shape=(2, 3, 9, 9)),     # post conv-transpose FIR
+        dict(f=f4, up=2, down=1, padding=[2, 1, 2, 1], flip_filter=False, gain=4.0, shape=(2, 3, 8, 8)),     # upsample2d
+        dict(f=f4, up=1, down=2, padding=[1, 1, 1, 1], flip_filter=False, gain=1.0, shape=(1, 4, 16, 12)),   # downsample2d
+        dict(f=f3, up=2, down=3, padding=[3, 0, 1, 2], flip_filter=True, gain=0.5, shape=(2, 2, 7, 10)),
+        dict(f=f2d, up=3, down=2, padding=[2, 2, 3, 1], flip_filter=False, gain=1.5, shape=(1, 3, 6, 5)),
+        dict(f=f2d, up=1, down=1, padding=[-1, 3, 2, -1], flip_filter=True, gain=1.0, shape=(1, 2, 9, 9)),   # crop
+    ]
+    for c in cases:
+        x = torch.randn(c["shape"], generator=g)
+        xr = x.clone().requires_grad_(True)
+        y = upfirdn2d.upfirdn2d(xr, c["f"], up=c["up"], down=c["down"], padding=c["padding"], flip_filter=c["flip_filter"],
+                                gain=c["gain"], impl="ref")
+        dy = torch.randn(y.shape, generator=g)
+        (dx,) = torch.autograd.grad(y, [xr], dy)
+        out["upfirdn2d"].append(dict(x=x, y=y.detach(), dy=dy, dx=dx, **{k: v for k, v in c.items() if k != "shape"}))
+    torch.save(out, os.path.join(GOLD, "ops_ref.pt"))
+    print("ops goldens:", len(out["bias_act"]), "bias_act,", len(out["upfirdn2d"]), "upfirdn2d")
+
+
+def gen_hungarian():
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.RandomState(7)
+    cases = []
+    for n in range(1, 10):
+        for rep in range(6):
+            m = rng.rand(n, n)
+            if rep == 3:
+                m = np.zeros((n, n))
+            if rep == 4:
+                m = np.round(m * 3) / 3          # ties
+            if rep == 5:
+                m = (rng.rand(n, n) > 0.6).astype(np.float64) * rng.rand(n, n)
+            r, c = linear_sum_assignment(m, maximize=True)
+            cases.append(dict(cost=torch.from_numpy(m.copy()), row=torch.from_numpy(r), col=torch.from_numpy(c)))
+    for (nr, nc) in [(3, 7), (7, 3), (9, 5), (1, 9)]:
+        m = rng.rand(nr, nc)
+        r, c = linear_sum_assignment(m, maximize=True)
+        cases.append(dict(cost=torch.from_numpy(m.copy()), row=torch.from_numpy(r), col=torch.from_numpy(c)))
+    torch.save(cases, os.path.join(GOLD, "hungarian_scipy.pt"))
+    print("hungarian goldens:", len(cases))
+
+
+def run_model_goldens(nd, G, D, name, batch, n_valid, seed):
+    inp = make_inputs(batch, n_valid=n_valid, seed=seed)
+    store = {}
+    hooks = [_hook_outputs(G.text_encoder, store, "G.text_encoder"), _hook_outputs(G.input_proj, store, "G.input_proj"),
+             _hook_outputs(G.transformer, store, "G.transformer"), _hook_outputs(G.fc_in, store, "G.fc_in"),
+             _hook_outputs(G.backbone[0].body, store, "G.backbone_body")]
+    out = {"inputs_seed": seed, "batch": batch, "n_valid": n_valid}
+    with torch.no_grad():
+        t = time.time()
+        res = G(inp["z"], inp["bbox_class"], inp["bbox_real"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"],
+                inp["background"], inp["c"], reconst=True)
+        print(name, "G fwd %.1fs" % (time.time() - t))
+        out["G"] = dict(zip(["bbox_fake", "loss_z", "logit_cls", "loss_lm", "loss_text_len"], [r.clone() for r in res]))
+        for h in hooks:
+            h.remove()
+        out["G_inter"] = {
+            "text_cls": store["G.text_encoder"][:, 0, :].clone(),                       # [B*9, 768]
+            "input_proj": store["G.input_proj"].to(torch.float16),                      # [B, 256, 8, 8]
+            "fc_in": store["G.fc_in"].clone(),
+            "hs": store["G.transformer"].clone(),                                       # [B, 9, 256]
+            "backbone_mean_abs": float(store["G.backbone_body"].abs().mean()),
+            "backbone_sub": store["G.backbone_body"][:, ::16].to(torch.float16),
+        }
+        t = time.time()
+        dres = D(inp["bbox_real"], inp["bbox_class"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"],
+                 inp["background"], inp["c"], reconst=True)
+        print(name, "D fwd %.1fs" % (time.time() - t))
+        names = ["logit_disc", "logit_disc_uncond", "bbox_pred", "logit_cls", "loss_lm", "loss_text_len", "bg_rec",
+                 "bbox_pred_uncond", "logit_cls_uncond"]
+        d = dict(zip(names, [r.clone() for r in dres]))
+        bg = d.pop("bg_rec")
+        d["bg_rec_sub"] = bg[:, :, ::8, ::8].clone()
+        d["bg_rec_mean"] = float(bg.mean())
+        d["bg_rec_std"] = float(bg.std())
+        out["D"] = d
+        fres = D(out["G"]["bbox_fake"], inp["bbox_class"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"],
+                 inp["background"], inp["c"])
+        out["D_fake"] = dict(logit_disc=fres[0].clone(), logit_disc_uncond=fres[1].clone())
+    torch.save(out, os.path.join(GOLD, name + ".pt"))
+    print("saved", name)
+
+
+def run_loss_goldens(nd, G, D, name, batch, n_valid, seed):
+    """Full reference loss + backward (training/loss.py accumulate_gradients) with dropout off."""
+    import training.loss as ref_loss
+    from torch_utils import training_stats
+    training_stats.report = lambda name, value: value          # stats collector needs init_multiprocessing
+    inp = make_inputs(batch, n_valid=n_valid, seed=seed)
+    loss = ref_loss.StyleGAN2Loss(device=torch.device("cpu"), G=G, D=D, r1_gamma=0.0, pl_weight=0.0)
+    out = {"inputs_seed": seed, "batch": batch, "n_valid": n_valid, "grads": {}}
+    for phase, mod, other in [("Gmain", G, D), ("Dmain", D, G)]:
+        for m in (G, D):
+            m.requires_grad_(False)
+            for p in m.parameters():
+                p.grad = None
+        mod.requires_grad_(True)
+        mod.text_encoder.requires_grad_(False)
+        t = time.time()
+        loss.accumulate_gradients(phase=phase, bbox_real=inp["bbox_real"], bbox_class=inp["bbox_class"], bbox_text=inp["bbox_text"],
+                                  bbox_patch=inp["bbox_patch"], padding_mask=inp["padding_mask"], background=inp["background"],
+                                  real_c=inp["c"], gen_z=inp["z"], gen_c=inp["c"], gain=1.0, cur_nimg=0)
+        print(name, phase, "fwd+bwd %.1fs" % (time.time() - t))
+        norms, small = {}, {}
+        for k, p in mod.named_parameters():
+            if p.grad is None:
+                continue
+            norms[k] = float(p.grad.norm())
+            if p.grad.numel() <= 4096:
+                small[k] = p.grad.clone()
+        out["grads"][phase] = dict(norms=norms, small=small)
+    torch.save(out, os.path.join(GOLD, name + ".pt"))
+    print("saved", name)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-loss", action="store_true")
+    ap.add_argument("--skip-model", action="store_true")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    nd = ref_shim.load()
+    torch.set_num_threads(os.cpu_count())
+    gen_ops()
+    gen_hungarian()
+    if args.skip_model:
+        return
+    torch.manual_seed(0)
+    G = nd.Generator(**ref_shim.G_KWARGS).eval()
+    D = nd.Discriminator(**ref_shim.D_KWARGS).eval()
+    synth_state_dict(G)
+    synth_state_dict(D)
+    manifest = {"G": {k: list(v.shape) for k, v in G.state_dict().items()},
+                "D": {k: list(v.shape) for k, v in D.state_dict().items()}}
+    with open(os.path.join(GOLD, "state_dict_manifest.json"), "w") as f:
+        json.dump(manifest, f)
+    run_model_goldens(nd, G, D, "model_b1_v4", batch=1, n_valid=4, seed=1)      # BASELINE configs[0]
+    run_model_goldens(nd, G, D, "model_b2_v8", batch=2, n_valid=8, seed=2)
+    if not args.skip_loss:
+        run_loss_goldens(nd, G, D, "loss_b2_v8", batch=2, n_valid=8, seed=2)
+
+
+if __name__ == "__main__":
+    main()
