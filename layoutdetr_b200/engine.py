@@ -9,7 +9,9 @@ import torch
 
 from . import kernels as K
 
-_shadow = {}          # (id(param), tag) -> (version, data_ptr, tensor)
+_shadow = {}          # (id(param), tag) -> (version, data_ptr, generation, tensor)
+_managed = {}         # id(param) -> bf16 [N, K] view kept fresh by the fused optimizer kernel (flat storage)
+_generation = {}      # id(param) -> int, bumped when a kernel rewrites the parameter through a raw pointer
 _SM_COUNT = None
 
 
@@ -22,6 +24,20 @@ def sm_count():
 
 def clear_cache():
     _shadow.clear()
+    _managed.clear()
+    _generation.clear()
+
+
+def register_managed(param, shadow):
+    """`shadow` (bf16 [N, K] view of the flat bf16 buffer) is rewritten together with `param` by ld_adam_flat /
+    ld_ema_flat, so it is always current."""
+    _managed[id(param)] = (param.data_ptr(), shadow)
+
+
+def bump_generation(params):
+    """Invalidate derived shadows (concatenations, conv re-layouts, padded copies) after an in-kernel update."""
+    for p in params:
+        _generation[id(p)] = _generation.get(id(p), 0) + 1
 
 
 def _lookup(key, params):
@@ -30,13 +46,15 @@ def _lookup(key, params):
         return None
     ver = tuple(p._version for p in params)
     ptr = tuple(p.data_ptr() for p in params)
-    if ent[0] == ver and ent[1] == ptr:
-        return ent[2]
+    gen = tuple(_generation.get(id(p), 0) for p in params)
+    if ent[0] == ver and ent[1] == ptr and ent[2] == gen:
+        return ent[3]
     return None
 
 
 def _store(key, params, value):
-    _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params), value)
+    _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
+                    tuple(_generation.get(id(p), 0) for p in params), value)
     return value
 
 
@@ -46,6 +64,9 @@ def pad8(n):
 
 def w_bf16(param):
     """bf16 shadow of a 2-D weight [N, K] with K zero-padded to a multiple of 8 (TMA stride rule)."""
+    man = _managed.get(id(param))
+    if man is not None and man[0] == param.data_ptr():
+        return man[1]
     key = (id(param), "w")
     v = _lookup(key, (param,))
     if v is None:

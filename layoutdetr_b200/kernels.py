@@ -394,3 +394,15 @@ def channel_dot(a, g, B, pixels, C):
     check(lib().ld_channel_dot(_p(a), c_int(dt(a)), _p(g), _p(out), c_int(B), c_int64(pixels), c_int(C), _stream()),
           "ld_channel_dot")
     return out
+
+
+def adam_flat(p, g, m, v, p16, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """Fused nan_to_num + Adam + bf16-shadow refresh over flat fp32 storage (numel % 4 == 0)."""
+    _cuda(p, g, v)
+    check(lib().ld_adam_flat(_p(p), _p(g), _p(m), _p(v), _p(p16), c_int64(p.numel()), c_float(lr), c_float(beta1),
+                             c_float(beta2), c_float(eps), c_int(step), c_float(grad_scale), _stream()), "ld_adam_flat")
+
+
+def ema_flat(p_ema, p, p_ema16, beta):
+    _cuda(p_ema, p)
+    check(lib().ld_ema_flat(_p(p_ema), _p(p), _p(p_ema16), c_int64(p.numel()), c_float(beta), _stream()), "ld_ema_flat")

@@ -1,0 +1,27 @@
+"""Box losses of the LayoutDETR training objective (mirror of the functions training/loss.py imports from the
+reference's metrics/metric_layoutnet.py: generalized_iou_loss :245-275, compute_overlap :153-179,
+compute_alignment :182-201) and the Hungarian max-IoU helpers (:100-126) on the lsap kernel.
+
+The three losses act on `[B, 9, 4]` boxes: negligible FLOPs, so they are evaluated by one fused CUDA kernel
+(forward + analytic backward) instead of ~60 eager launches.
+"""
+import torch
+
+from .. import box_ops
+
+
+def convert_xywh_to_ltrb(bbox):
+    xc, yc, w, h = bbox
+    return [xc - w / 2, yc - h / 2, xc + w / 2, yc + h / 2]
+
+
+def generalized_iou_loss(bbox_fake, bbox_real):
+    return box_ops.giou_loss(bbox_fake, bbox_real)
+
+
+def compute_overlap(bbox, mask):
+    return box_ops.overlap(bbox, mask)
+
+
+def compute_alignment(bbox, mask):
+    return box_ops.alignment(bbox, mask)

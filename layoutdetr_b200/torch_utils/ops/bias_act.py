@@ -85,7 +85,7 @@ def _make(dim, act, alpha, gain, clamp):
             if act != 'linear' or gain != 1 or clamp >= 0 or b is not None:
                 y = _launch(x, b, None, None, None, 0, dim, spec, alpha, gain, clamp)
             keep_x = 'x' in spec.ref or spec.has_2nd_grad
-            ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if 'y' in spec.ref else None)
+            ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if ('y' in spec.ref or clamp >= 0) else None)
             return y
 
         @staticmethod

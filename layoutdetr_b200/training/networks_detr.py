@@ -125,6 +125,23 @@ def _host_mask(padding_mask):
     return v
 
 
+_valid_idx_cache = {}
+
+
+def valid_index(padding_mask):
+    """(device int64 indices, numpy indices) of the valid (non-padding) slots of a `[B, N]` mask, row-major —
+    the sync-free equivalent of boolean indexing with `~padding_mask`."""
+    key = (padding_mask.data_ptr(), padding_mask._version, tuple(padding_mask.shape))
+    v = _valid_idx_cache.get(key)
+    if v is None:
+        if len(_valid_idx_cache) > 16:
+            _valid_idx_cache.clear()
+        cpu = np.flatnonzero(~_host_mask(padding_mask).reshape(-1))
+        v = (torch.from_numpy(cpu).to(padding_mask.device), cpu)
+        _valid_idx_cache[key] = v
+    return v
+
+
 def _encode_text(module, text, B, N):
     """CLS feature of the frozen/unfrozen text encoder for every slot -> bf16 [B*N, bert_f_dim]."""
     enc = module.text_encoder
@@ -251,8 +268,7 @@ class Generator(nn.Module):
         if not reconst:
             return bbox_fake
 
-        valid_cpu = np.flatnonzero(~_host_mask(padding_mask).reshape(-1))
-        valid = torch.from_numpy(valid_cpu).to(dev)
+        valid, valid_cpu = valid_index(padding_mask)
         xv = hs.index_select(0, valid)                                                              # [M, 256]
         z_rec = Fn.linear_f32(xv, self.fc_z_rec.weight, self.fc_z_rec.bias)
         z_tgt = z0.unsqueeze(1).expand(-1, N, -1).reshape(B * N, -1).index_select(0, valid)
@@ -387,8 +403,7 @@ class Discriminator(nn.Module):
         if not reconst:
             return logit_disc, logit_disc_uncond
 
-        valid_cpu = np.flatnonzero(~_host_mask(padding_mask).reshape(-1))
-        valid = torch.from_numpy(valid_cpu).to(dev)
+        valid, valid_cpu = valid_index(padding_mask)
         xv = self._decode_branch(x0, self.pos_token, self.dec_fc_in, self.dec_transformer, B, N, padding_mask, valid)
         bbox_pred = Fn.linear_f32(xv, self.bbox_embed.weight, self.bbox_embed.bias).sigmoid()
         logit_cls = Fn.linear_f32(xv, self.fc_out_cls.weight, self.fc_out_cls.bias)
