@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — LayoutDETR training-iteration throughput (layout samples/sec) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 16]
+
+A "step" is one full training iteration of the reference's hot loop (training/training_loop.py:274-328):
+Gmain (G fwd(reconst) + D fwd + backward + Adam) + Dmain (G fwd, D fwd x2, backward + Adam) + G_ema update, at
+16 samples per GPU, 256x256 backgrounds, 8 valid of 9 slots, text padded to 256 tokens (BASELINE.json configs[1]).
+Weak scaling: every rank runs its own 16 samples; gradients are all-reduced over NCCL each phase.
+
+Prints ONE JSON line (see the task contract).  `--impl reference` times the CPU oracle port of the same
+iteration on the host cores (the reference itself is PyTorch-on-CPU here; /root/reference does not exist on the
+GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("LAYOUTDETR_SYNTHETIC_TOKENIZER", "1")
+
+GFLOP_PER_SAMPLE = 3186.3          # dense fwd+bwd FLOPs of one training iteration, per sample
+METRIC = "layout samples/sec @ bs16 256^2 8-query (full G+D training iteration)"
+
+G_KWARGS = dict(z_dim=4, num_bbox_labels=8, img_channels=3, img_height=1024, img_width=1024, c_dim=0,
+                background_size=256, bert_f_dim=768, bert_num_heads=4, bert_num_encoder_layers=12,
+                bert_num_decoder_layers=2, im_f_dim=512)
+D_KWARGS = dict(num_bbox_labels=8, img_channels=3, img_height=1024, img_width=1024, c_dim=0,
+                background_size=256, bert_f_dim=768, bert_num_heads=4, bert_num_encoder_layers=12,
+                bert_num_decoder_layers=2, im_f_dim=512)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=reasons, samples=len(self.rows))
+
+
+# --------------------------------------------------------------------------------------------------------
+def cpu_iteration_seconds(batch, threads):
+    """One Gmain+Dmain fwd+bwd of the ORACLE (CPU port of the reference path) at `batch` samples."""
+    import torch
+    from layoutdetr_b200.synthetic import SyntheticTokenizer, make_inputs
+    from layoutdetr_b200.training import networks_detr as nd
+    from oracle import train_step
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    G = nd.Generator(**G_KWARGS)
+    D = nd.Discriminator(**D_KWARGS)
+    sdG = {k: v.detach() for k, v in G.state_dict().items()}
+    sdD = {k: v.detach() for k, v in D.state_dict().items()}
+    del G, D
+    inp = make_inputs(batch, n_valid=8, seed=1)
+    tok = SyntheticTokenizer()
+    t0 = time.time()
+    train_step.iteration(sdG, sdD, tok, inp)
+    return time.time() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = 1
+    times = []
+    for i in range(args.warmup_ref + args.steps_ref):
+        t = cpu_iteration_seconds(B, threads)
+        if i >= args.warmup_ref:
+            times.append(t)
+    sec = sum(times) / len(times)
+    v = B / sec
+    line = dict(metric=METRIC, value=v, unit="samples/s", n_gpus=args.gpus, steps=len(times), warmup=args.warmup_ref,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload="bs16 256x256 synthetic, 8 of 9 slots, G+D fwd/bwd (configs[1]); CPU arm runs a bounded sample", sample_batch=B),
+                cpu_baseline=dict(value=v, unit="samples/s", cores=threads, kind="port",
+                                  sample="%d sample(s) per step: oracle Gmain+Dmain fwd+bwd, dense T=256, fp32" % B),
+                e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------
+def gemm_roofline(torch, K, pk):
+    """Dominant kernel (gemm_bf16_kernel) on the dominant shape — the BERT FFN GEMM of one text-encoder call at bs16:
+    M = 16*9*256 tokens, N = 3072, K = 768 — timed alone with CUDA events on the launching stream."""
+    M, N, Kd = 16 * 9 * 256, 3072, 768
+    a = torch.randn((M, Kd), device="cuda").to(torch.bfloat16)
+    w = torch.randn((N, Kd), device="cuda").to(torch.bfloat16)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        K.linear(a, w, out=out)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K.linear(a, w, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    flops = 2.0 * M * N * Kd
+    ach = flops / (ms * 1e-3) / 1e12
+    return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=None,
+                kernel="gemm_bf16_kernel", shape=[M, N, Kd], ms=ms, peak_source=pk["src"] + " burst (kernel timed alone)")
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from layoutdetr_b200 import _lib, kernels as K
+    from layoutdetr_b200.synthetic import make_inputs
+    from layoutdetr_b200.training import networks_detr as nd
+    from layoutdetr_b200.training.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()        # fail loudly if the CUDA library is missing
+    pk = peaks()
+    B = args.batch
+
+    torch.manual_seed(0)                          # identical initial weights on every rank (reference broadcasts from rank 0)
+    G = nd.Generator(**G_KWARGS).to(dev)
+    D = nd.Discriminator(**D_KWARGS).to(dev)
+    for m in (G, D):
+        m.text_trim = args.text_trim
+        m.text_dedup = args.text_dedup
+    trainer = Trainer(G, D, dev, batch_size=B * world, num_gpus=world)
+
+    # ---- inputs: resident (value) and host-pinned rotating batches (e2e)
+    nb_host = 4
+    host_batches = [make_inputs(B, n_valid=8, seed=100 * rank + 1 + i) for i in range(nb_host)]
+    for hb in host_batches:
+        for k, v in hb.items():
+            if torch.is_tensor(v):
+                hb[k] = v.pin_memory()
+    resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host_batches[0].items()}
+    gz = torch.Generator(device=dev).manual_seed(1234 + rank)
+    zs = [torch.randn((B, 9, 4), device=dev, generator=gz) for _ in range(2)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        trainer.iteration(resident, zs[0], zs[1])
+
+    def step_e2e(i):
+        hb = host_batches[i % nb_host]
+        batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+        z1 = torch.randn((B, 9, 4), device=dev, generator=gz)
+        z2 = torch.randn((B, 9, 4), device=dev, generator=gz)
+        last = trainer.iteration(batch, z1, z2)
+        vals = torch.stack([v.float().mean() for v in last["Gmain"].values()] + [v.float().mean() for v in last["Dmain"].values()])
+        return vals.cpu()                                   # D2H read of the step's loss terms (synchronises)
+
+    # ---- warm-up (also builds caches / cuBLAS-free: nothing to autotune)
+    for i in range(args.warmup):
+        step_resident()
+    sync_all()
+
+    # ---- timed: resident inputs
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.launch_count_reset()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()                                       # flush L2 between timed iterations
+        ev[i][0].record()
+        step_resident()
+        ev[i][1].record()
+    sync_all()
+    clocks = sampler.stop()
+    launches = _lib.launch_count()
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([ms_dev], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- timed: end to end through the public API with host buffers (H2D of the batch + D2H of the losses)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values() if torch.is_tensor(v))
+    for i in range(2):
+        step_e2e(i)
+    sync_all()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        out = step_e2e(i + 2)
+        d2h = out.numel() * out.element_size()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = B * world / float(te.item())
+
+    if rank == 0:
+        roof = gemm_roofline(torch, K, pk)
+        step_tflops = value * GFLOP_PER_SAMPLE * 1e9 / 1e12 / world
+        roof["step"] = dict(achieved=step_tflops, peak=pk["sustained"], unit="TFLOP/s (algorithmic, dense reference shapes, per GPU)",
+                            frac=step_tflops / pk["sustained"], gflop_per_sample=GFLOP_PER_SAMPLE)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec = cpu_iteration_seconds(1, threads)
+            cpu = dict(value=1.0 / sec, unit="samples/s", cores=threads, kind="port",
+                       sample="1 sample: oracle Gmain+Dmain fwd+bwd, dense T=256, fp32 (%.1f s)" % sec)
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="bs16 256x256 synthetic, 8 of 9 slots, G+D fwd/bwd + Adam + EMA (BASELINE configs[1])",
+                                batch_per_gpu=B, global_batch=B * world, text_tokens=256, text_trim=bool(args.text_trim),
+                                text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
+                                dropout="off (deterministic eval-semantics kernels)", parallelism="dp%d" % world),
+                    clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU")
+    ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
+    ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--steps-ref", type=int, default=1)
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps_ref = max(1, min(args.steps, 2))
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

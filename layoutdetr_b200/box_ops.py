@@ -28,7 +28,7 @@ def giou_loss(fake, real):
 
 def overlap(bbox, mask):
     """[B]: sum_{i != j} area(i ∩ j) / area(i) over valid slots, divided by the number of valid slots."""
-    bbox = bbox * mask.unsqueeze(-1).to(bbox.dtype)
+    bbox = bbox.masked_fill(~mask.unsqueeze(-1), 0)          # masked_fill (not *0): its backward stops the 0/0 NaNs of padded slots
     l, t, r, b = _ltrb(bbox)
     area = (r - l) * (b - t)
     iw = torch.minimum(r[:, :, None], r[:, None, :]) - torch.maximum(l[:, :, None], l[:, None, :])

@@ -13,7 +13,7 @@ from . import kernels as K
 
 
 class FlatParams:
-    def __init__(self, module, exclude_prefixes=("text_encoder.",), beta1=0.0):
+    def __init__(self, module, exclude_prefixes=("text_encoder.",), beta1=0.0, with_grad=True):
         named = [(n, p) for n, p in module.named_parameters() if not n.startswith(tuple(exclude_prefixes))]
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
@@ -24,9 +24,9 @@ class FlatParams:
             total += (p.numel() + 7) // 8 * 8            # 32-byte aligned fp32 / 16-byte aligned bf16 views
         self.offsets, self.numel = offs, total
         self.p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(total, dtype=torch.float32, device=dev) if beta1 != 0.0 else None
+        self.g = torch.zeros(total, dtype=torch.float32, device=dev) if with_grad else None
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev) if with_grad else None
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev) if (beta1 != 0.0 and with_grad) else None
         self.p16 = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.step = 0
         with torch.no_grad():
@@ -34,7 +34,7 @@ class FlatParams:
                 n = p.numel()
                 self.p[o:o + n].copy_(p.detach().reshape(-1))
                 p.data = self.p[o:o + n].view(p.shape)
-                p.grad = self.g[o:o + n].view(p.shape)
+                p.grad = self.g[o:o + n].view(p.shape) if with_grad else None
             self.p16.copy_(K.to_bf16(self.p))
         for p, o in zip(self.params, offs):
             if p.ndim == 2 and p.shape[1] % 8 == 0:

@@ -465,9 +465,10 @@ class Conv2dFn(torch.autograd.Function):
         out = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
         K.gemm(M, Cout, cols.shape[1], K.Op(cols, cols.stride(0)), K.Op(w16, w16.stride(0)), K.Out(out, Cout),
                act=act, R=K.Out(residual, residual.stride(0)) if residual is not None else None,
-               col_scale=scale, col_bias=shift)
+               col_scale=scale, col_bias=shift.detach() if shift is not None else None)
         ctx.geom = (B, H, W, stride, pad, Ho, Wo, direct)
         ctx.weight, ctx.act, ctx.scale = weight, act, scale
+        ctx.shift_param = shift if isinstance(shift, torch.nn.Parameter) else None
         ctx.has_res = residual is not None
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, out if act != K.ACT_NONE else None)
@@ -482,6 +483,8 @@ class Conv2dFn(torch.autograd.Function):
         dy = dy.contiguous()
         dpre = K.act_bwd(dy, out, ctx.act) if ctx.act != K.ACT_NONE else dy
         dres = dpre if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        if ctx.shift_param is not None and ctx.needs_input_grad[3]:
+            _bgrad(ctx.shift_param, 0, Cout, dpre)
         dconv = dpre
         if ctx.scale is not None:
             dconv = K.scale_channels(dpre, ctx.scale, torch.bfloat16, dpre.numel(), Cout)
