@@ -209,6 +209,13 @@ def run_ours(args):
         step_resident()
     sync_all()
 
+    if args.ncu:                                            # one profiled step: ncu --profile-from-start off
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     # ---- timed: resident inputs
     sampler = ClockSampler(local)
     sampler.start()
@@ -273,13 +280,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU")
     ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profile exactly one resident step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)
     args = ap.parse_args()

@@ -90,6 +90,13 @@ typedef struct ld_gemm_desc {
     const float* col_scale; const float* col_bias;
     int64_t col_sb1, col_sb2;    /* batch strides of col_scale/col_bias (0 = shared) */
     const float* alpha_dev;      /* optional device scalar multiplied into alpha (upstream loss gradient) */
+    /* fused attention-probability epilogue (requires N <= 256, bf16 D, store-only):
+     *   D[m, :] = softmax_n(acc[m, n] * alpha + (key_mask[b1, n] ? mask_value : 0) + (causal && n > m ? mask_value : 0))
+     * mask_value = -10000 (BERT additive mask, training/med.py:651-654) or -inf (nn.MultiheadAttention key_padding_mask). */
+    int32_t softmax, causal;
+    float mask_value;
+    int32_t _pad2;
+    const uint8_t* key_mask;     /* [nb1, N], 1 = masked, or NULL */
 } ld_gemm_desc;
 
 int ld_gemm_bf16(const ld_gemm_desc* desc, void* stream);

@@ -59,10 +59,23 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
     lo = __low2float(h); hi = __high2float(h);
 }
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. fp32-level): one rcp + one ex2 + 6 FMA instead of
+// erff's branchy polynomial — the GELU epilogue runs inside the GEMM's TMEM drain.
+__device__ __forceinline__ float fast_erf(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float y = fmaf(1.061405429f, t, -1.453152027f);
+    y = fmaf(y, t, 1.421413741f);
+    y = fmaf(y, t, -0.284496736f);
+    y = fmaf(y, t, 0.254829592f);
+    y = 1.0f - y * t * __expf(-ax * ax);
+    return copysignf(y, x);
+}
+
 // exact (erf) GELU as used by BERT "gelu" (reference training/med.py:301, ACT2FN['gelu'])
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
 }

@@ -164,6 +164,26 @@ __global__ void act_bwd_kernel(const TG* __restrict__ dy, const TR* __restrict__
     }
 }
 
+// y = act(x) * gain for activations that could not be fused into a GEMM epilogue (training-mode GELU keeps the
+// pre-activation as the GEMM output and applies the activation here)
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n8, int act, float gain) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4*>(x)[i];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float lo, hi;
+            unpack_bf16x2(w[k], lo, hi);
+            if (act == LD_ACT_GELU) { lo = gelu_erf(lo); hi = gelu_erf(hi); }
+            else if (act == LD_ACT_RELU) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            else if (act == LD_ACT_LRELU) { lo = lo > 0.f ? lo : 0.2f * lo; hi = hi > 0.f ? hi : 0.2f * hi; }
+            o[k] = pack_bf16x2(lo * gain, hi * gain);
+        }
+        reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // column sums of a [rows, cols] matrix accumulated into out[cols] (bias gradients)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long ld, float* __restrict__ out, long rows, int cols, int rows_per_block) {
@@ -287,6 +307,15 @@ int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, voi
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ref, (__nv_bfloat16*)dx, n, act, gain);
     ld::count_launch();
     LD_LAUNCH_CHECK("act_bwd");
+    return 0;
+}
+
+int ld_act_fwd_bf16(const void* x, void* y, int64_t n, int act, float gain, void* stream) {
+    LD_CHECK_ARG(x && y && n > 0 && n % 8 == 0, "act_fwd: n must be a positive multiple of 8");
+    LD_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "act_fwd: pointers must be 16-byte aligned");
+    act_fwd_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, act, gain);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("act_fwd");
     return 0;
 }
 

@@ -2,8 +2,10 @@
 // 128 x {128,256} x 16 UMMA, fp32 accumulators double-buffered in TMEM) -> fused epilogue.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).  The accumulator of tile i+1 is
-// produced while the epilogue drains tile i.
+// allocator, warps 4..11 = epilogue (two warps per TMEM lane quadrant, each taking half of the tile's
+// columns).  The accumulator of tile i+1 is produced while the epilogue drains tile i.  The common
+// epilogues (per-column scale/bias staged in smem, activation, residual, bf16/fp32 vector stores) are
+// compile-time specialised; rare ones (aux copy, accumulate, unaligned rows) take a generic path.
 //
 // Operand "major" flags let one kernel serve forward (A K-major, B K-major), dgrad (B MN-major) and
 // wgrad (A and B MN-major) without materialising transposes; two batch dims with arbitrary strides
@@ -24,7 +26,10 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_STAGE_BYTES_MAX = 256 * BK * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES_MAX;
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+constexpr int EPI_STAGE_BYTES = 2 * 2 * 256 * 4;    // [acc stage][scale|bias][256] fp32
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024 for manual alignment
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;                     // TMEM columns per accumulator stage
 
@@ -34,12 +39,14 @@ struct KParams {
     int a_mn, b_mn;
     int m_tiles, n_tiles, kb_total, kb_per_split, total_tiles;
     int vec_ok;
+    int fast;        // compile-time specialised epilogue usable (aligned rows, store-only, no aux)
     float alpha, post_gain;
     void* D; long ldd, d_sb1, d_sb2;
     void* aux;
     const void* R; long ldr, r_sb1, r_sb2;
     const float* cs; const float* cb; long col_sb1, col_sb2;
     const float* alpha_dev;
+    int softmax, causal; float mask_value; const uint8_t* key_mask;
 };
 
 struct Tile {
@@ -60,6 +67,15 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
     return tl;
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+    if (ACT == LD_ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == LD_ACT_GELU) return gelu_erf(v);
+    if (ACT == LD_ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
+    if (ACT == LD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+    return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case LD_ACT_RELU:    return fmaxf(v, 0.0f);
@@ -70,7 +86,253 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+
+// Generic (slow-path) epilogue for one 16-column chunk held in registers: every feature, scalar fallbacks.
+__device__ __forceinline__ void epilogue_generic_chunk(const KParams& p, const uint32_t (&r)[16], float alpha, int n_base,
+                                                       long d_off, long r_off, long c_off) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+    const bool full_chunk = (n_base + 16 <= p.N);
+    if (p.cs) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] *= __ldg(p.cs + c_off + n_base + i);
+    }
+    if (p.cb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += __ldg(p.cb + c_off + n_base + i);
+    }
+    const bool vec = p.vec_ok && full_chunk;
+    if (p.R) {
+        if (p.r_dtype == LD_BF16) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base;
+            if (vec) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { float lo, hi; unpack_bf16x2(w[i], lo, hi); v[2 * i] += lo; v[2 * i + 1] += hi; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += bf16_to_f32(rp[i]);
+            }
+        } else {
+            const float* rp = reinterpret_cast<const float*>(p.R) + r_off + n_base;
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(rp) + i);
+        v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += rp[i];
+            }
+        }
+    }
+    if (p.aux) {
+        if (p.d_dtype == LD_BF16) {
+            __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + d_off + n_base;
+            if (vec) {
+                uint4 a, b;
+                a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+                b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+                reinterpret_cast<uint4*>(ap)[0] = a; reinterpret_cast<uint4*>(ap)[1] = b;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n_base + i < p.N) ap[i] = f32_to_bf16(v[i]);
+            }
+        } else {
+            float* ap = reinterpret_cast<float*>(p.aux) + d_off + n_base;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) ap[i] = v[i];
+        }
+    }
+    if (p.act != LD_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
+    }
+    if (p.post_gain != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= p.post_gain;
+    }
+    if (p.d_dtype == LD_BF16) {
+        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n_base;
+        if (p.accumulate == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += bf16_to_f32(dp[i]);
+        }
+        if (vec) {
+            uint4 a, b;
+            a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
+            b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+            reinterpret_cast<uint4*>(dp)[0] = a; reinterpret_cast<uint4*>(dp)[1] = b;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = f32_to_bf16(v[i]);
+        }
+    } else {
+        float* dp = reinterpret_cast<float*>(p.D) + d_off + n_base;
+        if (p.accumulate == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) atomicAdd(dp + i, v[i]);
+        } else {
+            if (p.accumulate == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += dp[i];
+            }
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(dp)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = v[i];
+            }
+        }
+    }
+}
+
+// Fast-path epilogue for 32 columns of one row: v = act(acc*alpha*cs + cb (+R)) * gain -> 128-bit stores.
+template <int ACT, bool OUT_BF16, int RES>   // RES: 0 none, 1 bf16, 2 fp32
+__device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint32_t (&r)[32], float alpha, const float* cs_s,
+                                                    const float* cb_s, int c0, int n_base, long d_off, long r_off) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]) * alpha, cs_s[c0 + i], cb_s[c0 + i]);
+    if (RES == 1) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 a = __ldg(rp + j);
+            float lo, hi;
+            unpack_bf16x2(a.x, lo, hi); v[8 * j + 0] += lo; v[8 * j + 1] += hi;
+            unpack_bf16x2(a.y, lo, hi); v[8 * j + 2] += lo; v[8 * j + 3] += hi;
+            unpack_bf16x2(a.z, lo, hi); v[8 * j + 4] += lo; v[8 * j + 5] += hi;
+            unpack_bf16x2(a.w, lo, hi); v[8 * j + 6] += lo; v[8 * j + 7] += hi;
+        }
+    } else if (RES == 2) {
+        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + r_off + n_base);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(rp + j);
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        }
+    }
+    if (ACT != LD_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
+    }
+    const float gain = p.post_gain;
+    if (OUT_BF16) {
+        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n_base);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * j + 0] * gain, v[8 * j + 1] * gain); o.y = pack_bf16x2(v[8 * j + 2] * gain, v[8 * j + 3] * gain);
+            o.z = pack_bf16x2(v[8 * j + 4] * gain, v[8 * j + 5] * gain); o.w = pack_bf16x2(v[8 * j + 6] * gain, v[8 * j + 7] * gain);
+            dp[j] = o;
+        }
+    } else {
+        float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n_base);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j] * gain, v[4 * j + 1] * gain, v[4 * j + 2] * gain, v[4 * j + 3] * gain);
+    }
+}
+
+template <int ACT, bool OUT_BF16, int RES>
+__device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile& tl, uint32_t taddr, int col_begin, int col_end,
+                                                   bool row_ok, float alpha, const float* cs_s, const float* cb_s,
+                                                   long d_off, long r_off, long c_off) {
+    for (int c0 = col_begin; c0 < col_end; c0 += 32) {
+        const int n_base = tl.n0 + c0;
+        if (n_base >= p.N) break;                       // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(taddr + c0, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        if (n_base + 32 <= p.N) {
+            epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, r, alpha, cs_s, cb_s, c0, n_base, d_off, r_off);
+        } else {                                        // ragged last chunk of the matrix: scalar path
+            uint32_t h[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = r[i];
+            epilogue_generic_chunk(p, h, alpha, n_base, d_off, r_off, c_off);
+            if (n_base + 16 < p.N) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = r[16 + i];
+                epilogue_generic_chunk(p, h, alpha, n_base + 16, d_off, r_off, c_off);
+            }
+        }
+    }
+}
+
+
+// Fused attention-probability epilogue: the whole key axis of a query row sits in this thread's TMEM lane, so
+// scale + mask + softmax + bf16 cast happen in the drain and the fp32 score matrix never reaches HBM.
+// Three sweeps over TMEM (max, sum, write); add_s = per-key additive mask staged in smem.
+__device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Tile& tl, uint32_t taddr, bool row_ok, int row,
+                                                      float scale, const float* add_s, long d_off) {
+    const int N = p.N;
+    const int nch = (N + 31) >> 5;
+    const float neg = p.mask_value;
+    float mx = -INFINITY;
+    for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int c = ch * 32 + i;
+            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            if (p.causal && c > row) v += neg;
+            if (c < N) mx = fmaxf(mx, v);
+        }
+    }
+    float sum = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int c = ch * 32 + i;
+            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            if (p.causal && c > row) v += neg;
+            if (c < N) sum += __expf(v - mx);
+        }
+    }
+    const float inv = __fdividef(1.0f, sum);
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off;
+    const int n_pad = (N + 7) & ~7;
+    for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int c = ch * 32 + i;
+            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            if (p.causal && c > row) v += neg;
+            e[i] = (c < N) ? __expf(v - mx) * inv : 0.f;
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = ch * 32 + 8 * j;
+                if (c < n_pad) {
+                    uint4 o;
+                    o.x = pack_bf16x2(e[8 * j + 0], e[8 * j + 1]); o.y = pack_bf16x2(e[8 * j + 2], e[8 * j + 3]);
+                    o.z = pack_bf16x2(e[8 * j + 4], e[8 * j + 5]); o.w = pack_bf16x2(e[8 * j + 6], e[8 * j + 7]);
+                    *reinterpret_cast<uint4*>(dp + c) = o;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,7 +351,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -165,127 +427,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue
-        const int q = warp & 3;                       // TMEM lane quadrant of this warp
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int e = warp - 4;
+        const int q = e & 3;                          // TMEM lane quadrant of this warp (hardware: warp_id % 4)
+        const int half = e >> 2;                      // which half of the tile's columns
+        const int et = threadIdx.x - 128;             // 0..255 within the epilogue group
+        float* epi_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
         int as = 0; uint32_t aphase = 0;
         const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+        const int col_begin = half * (p.bn >> 1), col_end = col_begin + (p.bn >> 1);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const Tile tl = decode_tile(p, t);
+            const long c_off = (long)tl.b1 * p.col_sb1 + (long)tl.b2 * p.col_sb2;
+            float* cs_s = epi_s + as * 512;
+            float* cb_s = cs_s + 256;
+            if (p.softmax) {                          // stage the additive key mask of this batch
+                const uint8_t* km = p.key_mask ? p.key_mask + (long)tl.b1 * p.N : nullptr;
+                cs_s[et] = (km && et < p.N && km[et]) ? p.mask_value : 0.0f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            } else if (p.fast) {                      // stage per-column scale / bias of this tile
+                const int n = tl.n0 + et;
+                const bool ok = et < p.bn && n < p.N;
+                cs_s[et] = (ok && p.cs) ? __ldg(p.cs + c_off + n) : 1.0f;
+                cb_s[et] = (ok && p.cb) ? __ldg(p.cb + c_off + n) : 0.0f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const int row = tl.m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
             const long d_off = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2 + (long)row * p.ldd;
             const long r_off = (long)tl.b1 * p.r_sb1 + (long)tl.b2 * p.r_sb2 + (long)row * p.ldr;
-            const long c_off = (long)tl.b1 * p.col_sb1 + (long)tl.b2 * p.col_sb2;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
-            for (int c0 = 0; c0 < p.bn; c0 += 16) {
-                const int n_base = tl.n0 + c0;
-                if (n_base >= p.N) break;             // warp-uniform
-                uint32_t r[16];
-                tmem_ld_x16(taddr + c0, r);
-                tmem_ld_wait();
-                if (!row_ok) continue;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-                const bool full_chunk = (n_base + 16 <= p.N);
-                if (p.cs) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] *= __ldg(p.cs + c_off + n_base + i);
+            if (p.softmax) {
+                if (half == 0) epilogue_softmax_tile(p, tl, taddr, row_ok, row, alpha, cs_s, d_off);
+            } else if (p.fast) {
+#define LD_EPI(ACT, BF, RES) epilogue_fast_tile<ACT, BF, RES>(p, tl, taddr, col_begin, col_end, row_ok, alpha, cs_s, cb_s, d_off, r_off, c_off)
+#define LD_EPI_ACT(BF, RES)                                           \
+                switch (p.act) {                                      \
+                    case LD_ACT_RELU:    LD_EPI(LD_ACT_RELU, BF, RES); break;    \
+                    case LD_ACT_GELU:    LD_EPI(LD_ACT_GELU, BF, RES); break;    \
+                    case LD_ACT_LRELU:   LD_EPI(LD_ACT_LRELU, BF, RES); break;   \
+                    case LD_ACT_SIGMOID: LD_EPI(LD_ACT_SIGMOID, BF, RES); break; \
+                    default:             LD_EPI(LD_ACT_NONE, BF, RES); break;    \
                 }
-                if (p.cb) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += __ldg(p.cb + c_off + n_base + i);
-                }
-                const bool vec = p.vec_ok && full_chunk;
-                if (p.R) {
-                    if (p.r_dtype == LD_BF16) {
-                        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base;
-                        if (vec) {
-                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
-                            const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { float lo, hi; unpack_bf16x2(w[i], lo, hi); v[2 * i] += lo; v[2 * i + 1] += hi; }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += bf16_to_f32(rp[i]);
-                        }
-                    } else {
-                        const float* rp = reinterpret_cast<const float*>(p.R) + r_off + n_base;
-                        if (vec) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float4 a = __ldg(reinterpret_cast<const float4*>(rp) + i);
-                                v[4 * i] += a.x; v[4 * i + 1] += a.y; v[4 * i + 2] += a.z; v[4 * i + 3] += a.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) v[i] += rp[i];
-                        }
-                    }
-                }
-                if (p.aux) {
-                    if (p.d_dtype == LD_BF16) {
-                        __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + d_off + n_base;
-                        if (vec) {
-                            uint4 a, b;
-                            a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
-                            b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-                            reinterpret_cast<uint4*>(ap)[0] = a; reinterpret_cast<uint4*>(ap)[1] = b;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) ap[i] = f32_to_bf16(v[i]);
-                        }
-                    } else {
-                        float* ap = reinterpret_cast<float*>(p.aux) + d_off + n_base;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) ap[i] = v[i];
-                    }
-                }
-                if (p.act != LD_ACT_NONE) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act);
-                }
-                if (p.post_gain != 1.0f) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= p.post_gain;
-                }
+                const int res = p.R ? (p.r_dtype == LD_BF16 ? 1 : 2) : 0;
                 if (p.d_dtype == LD_BF16) {
-                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n_base;
-                    if (p.accumulate == 1) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += bf16_to_f32(dp[i]);
-                    }
-                    if (vec) {
-                        uint4 a, b;
-                        a.x = pack_bf16x2(v[0], v[1]);   a.y = pack_bf16x2(v[2], v[3]);   a.z = pack_bf16x2(v[4], v[5]);   a.w = pack_bf16x2(v[6], v[7]);
-                        b.x = pack_bf16x2(v[8], v[9]);   b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-                        reinterpret_cast<uint4*>(dp)[0] = a; reinterpret_cast<uint4*>(dp)[1] = b;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = f32_to_bf16(v[i]);
-                    }
+                    if (res == 0) { LD_EPI_ACT(true, 0) } else if (res == 1) { LD_EPI_ACT(true, 1) } else { LD_EPI(LD_ACT_NONE, true, 2); }
                 } else {
-                    float* dp = reinterpret_cast<float*>(p.D) + d_off + n_base;
-                    if (p.accumulate == 2) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) atomicAdd(dp + i, v[i]);
-                    } else {
-                        if (p.accumulate == 1) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) if (full_chunk || n_base + i < p.N) v[i] += dp[i];
-                        }
-                        if (vec) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                reinterpret_cast<float4*>(dp)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) if (n_base + i < p.N) dp[i] = v[i];
-                        }
-                    }
+                    if (res == 0) { LD_EPI(LD_ACT_NONE, false, 0); } else if (res == 1) { LD_EPI(LD_ACT_NONE, false, 1); } else { LD_EPI(LD_ACT_NONE, false, 2); }
+                }
+#undef LD_EPI_ACT
+#undef LD_EPI
+            } else {
+                for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+                    const int n_base = tl.n0 + c0;
+                    if (n_base >= p.N) break;         // warp-uniform
+                    uint32_t r[16];
+                    tmem_ld_x16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    epilogue_generic_chunk(p, r, alpha, n_base, d_off, r_off, c_off);
                 }
             }
             tc_fence_before();
@@ -335,6 +537,10 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     LD_CHECK_ARG(d->accumulate != 2 || d->d_dtype == LD_F32, "gemm: atomic accumulation needs fp32 output");
     LD_CHECK_ARG(d->d_dtype == LD_F32 || d->d_dtype == LD_BF16, "gemm: bad d_dtype %d", d->d_dtype);
     LD_CHECK_ARG(d->block_n == 0 || d->block_n == 128 || d->block_n == 256, "gemm: block_n must be 0/128/256");
+    LD_CHECK_ARG(!d->softmax || (d->N <= 256 && d->d_dtype == LD_BF16 && d->accumulate == 0 && d->split_k == 1 && !d->aux && !d->R &&
+                                 !d->col_scale && !d->col_bias && d->act == LD_ACT_NONE && d->ldd % 8 == 0 && d->d_sb1 % 8 == 0 &&
+                                 d->d_sb2 % 8 == 0 && ((uintptr_t)d->D & 15) == 0),
+                 "gemm: fused softmax epilogue needs N <= 256, aligned bf16 store-only output and no other epilogue terms");
 
     KParams p{};
     p.M = d->M; p.N = d->N; p.K = d->K; p.nb1 = d->nb1; p.nb2 = d->nb2;
@@ -347,11 +553,13 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     p.R = d->R; p.ldr = d->ldr; p.r_sb1 = d->r_sb1; p.r_sb2 = d->r_sb2;
     p.cs = d->col_scale; p.cb = d->col_bias; p.col_sb1 = d->col_sb1; p.col_sb2 = d->col_sb2;
     p.alpha_dev = d->alpha_dev;
+    p.softmax = d->softmax ? 1 : 0; p.causal = d->causal ? 1 : 0; p.mask_value = d->mask_value; p.key_mask = d->key_mask;
 
     const int sms = sm_count();
     p.m_tiles = ceil_div(p.M, BM);
     const long nb = (long)p.nb1 * p.nb2;
     int bn = d->block_n;
+    if (d->softmax) bn = d->N > 128 ? 256 : 128;      // the whole key axis in one tile
     if (bn == 0) {
         const long tiles256 = nb * p.m_tiles * ceil_div(p.N, 256) * p.split_k;
         bn = (p.N > 128 && tiles256 >= sms) ? 256 : 128;
@@ -376,6 +584,10 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     if (p.aux && !aligned(p.aux, p.ldd, p.d_sb1, p.d_sb2, d_es)) p.vec_ok = 0;
     if (p.R && !aligned(p.R, p.ldr, p.r_sb1, p.r_sb2, p.r_dtype == LD_BF16 ? 2 : 4)) p.vec_ok = 0;
 
+    // fast epilogue: vector stores, plain store, no aux; activations only with bf16 output and non-fp32 residual
+    p.fast = (p.vec_ok && p.accumulate == 0 && !p.aux &&
+              (p.act == LD_ACT_NONE || (p.d_dtype == LD_BF16 && !(p.R && p.r_dtype == LD_F32)))) ? 1 : 0;
+
     alignas(64) CUtensorMap tmA, tmB;
     int e = make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
     if (e) return e;
@@ -389,7 +601,7 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
         attr_set = true;
     }
     const int grid = (int)(total < sms ? total : sms);
-    gemm_bf16_kernel<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
     count_launch();
     LD_LAUNCH_CHECK("gemm launch");
     return 0;

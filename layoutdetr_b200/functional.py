@@ -103,9 +103,15 @@ class LinearFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         aux = None
-        if act == K.ACT_GELU and need_grad:
-            aux = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
-        K.linear(x, w16, b, act=act, residual=residual, out=out, aux=aux, post_gain=post_gain)
+        if act == K.ACT_GELU and need_grad and (M * N) % 8 == 0:
+            # keep the pre-activation (GELU' needs it): GEMM writes it through the fast epilogue, GELU is one extra pass
+            aux = out
+            K.linear(x, w16, b, act=K.ACT_NONE, residual=residual, out=aux)
+            out = K.act_fwd(aux, act, post_gain)
+        else:
+            if act == K.ACT_GELU and need_grad:
+                aux = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+            K.linear(x, w16, b, act=act, residual=residual, out=out, aux=aux, post_gain=post_gain)
         ctx.act, ctx.post_gain, ctx.row0, ctx.row1 = act, post_gain, row0, row1
         ctx.weight, ctx.bias = weight, bias
         ctx.has_res = residual is not None
@@ -298,13 +304,19 @@ class AttentionFn(torch.autograd.Function):
     def forward(ctx, q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal):
         dev = q_t.device
         Lkp = E.pad8(Lk)
-        S = torch.empty((B * H, Lq, Lk), dtype=torch.float32, device=dev)
         ldq, ldk, ldv = q_t.stride(0), k_t.stride(0), v_t.stride(0)
-        K.gemm(Lq, Lk, d, K.Op(q_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d),
-               K.Out(S, Lk, sb1=H * Lq * Lk, sb2=Lq * Lk), nb1=B, nb2=H)
         P = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
-        K.softmax_fwd(S, P, B, H, Lq, Lk, scale, key_mask=key_mask, mask_inf=mask_inf, causal=causal)
-        del S
+        if Lk <= 256:
+            # scores never leave the SM: scale + mask + softmax + bf16 cast run in the GEMM's TMEM drain
+            K.gemm(Lq, Lk, d, K.Op(q_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d),
+                   K.Out(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), nb1=B, nb2=H, alpha=scale,
+                   softmax=dict(key_mask=key_mask, mask_inf=mask_inf, causal=causal))
+        else:
+            S = torch.empty((B * H, Lq, Lk), dtype=torch.float32, device=dev)
+            K.gemm(Lq, Lk, d, K.Op(q_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d),
+                   K.Out(S, Lk, sb1=H * Lq * Lk, sb2=Lq * Lk), nb1=B, nb2=H)
+            K.softmax_fwd(S, P, B, H, Lq, Lk, scale, key_mask=key_mask, mask_inf=mask_inf, causal=causal)
+            del S
         O = torch.empty((B * Lq, H * d), dtype=torch.bfloat16, device=dev)
         K.gemm(Lq, d, Lk, K.Op(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d, mn=True),
                K.Out(O, H * d, sb1=Lq * H * d, sb2=d), nb1=B, nb2=H)

@@ -51,7 +51,8 @@ class _GemmDesc(ctypes.Structure):
                 ("aux", c_void_p),
                 ("R", c_void_p), ("ldr", c_int64), ("r_sb1", c_int64), ("r_sb2", c_int64),
                 ("col_scale", c_void_p), ("col_bias", c_void_p), ("col_sb1", c_int64), ("col_sb2", c_int64),
-                ("alpha_dev", c_void_p)]
+                ("alpha_dev", c_void_p),
+                ("softmax", c_int32), ("causal", c_int32), ("mask_value", c_float), ("_pad2", c_int32), ("key_mask", c_void_p)]
 
 
 class Op:
@@ -80,7 +81,7 @@ class Out:
 
 
 def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0, accumulate=0, split_k=1,
-         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None):
+         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None, softmax=None):
     """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics."""
     _cuda(A.t, B.t, D.t)
     d = _GemmDesc()
@@ -108,6 +109,14 @@ def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0,
     if alpha_dev is not None:
         assert alpha_dev.dtype == torch.float32
         d.alpha_dev = alpha_dev.data_ptr()
+    if softmax is not None:            # dict(key_mask=uint8 [nb1, N] or None, mask_inf=bool, causal=bool)
+        d.softmax = 1
+        d.causal = 1 if softmax.get("causal") else 0
+        d.mask_value = float("-inf") if softmax.get("mask_inf") else -10000.0
+        km = softmax.get("key_mask")
+        if km is not None:
+            assert km.dtype == torch.uint8 and km.is_contiguous()
+            d.key_mask = km.data_ptr()
     check(lib().ld_gemm_bf16(ctypes.byref(d), _stream()), "ld_gemm_bf16")
 
 
@@ -275,6 +284,13 @@ def act_bwd(dy, ref, act, gain=1.0):
     check(lib().ld_act_bwd(_p(dy), c_int(dt(dy)), _p(ref), c_int(dt(ref)), _p(dx), c_int(dt(dx)), c_int64(dy.numel()),
                            c_int(act), c_float(gain), _stream()), "ld_act_bwd")
     return dx
+
+
+def act_fwd(x, act, gain=1.0):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib().ld_act_fwd_bf16(_p(x), _p(y), c_int64(x.numel()), c_int(act), c_float(gain), _stream()), "ld_act_fwd_bf16")
+    return y
 
 
 def colsum_accum(x, out):
