@@ -27,7 +27,8 @@ constexpr int B_STAGE_BYTES_MAX = 256 * BK * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES_MAX;
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 2 * 2 * 256 * 4;    // [acc stage][scale|bias][256] fp32
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // +1024 for manual alignment
+constexpr int EPI_XPOSE_BYTES = 8 * 2048;           // per epilogue warp: 32 rows x 64 B transpose buffer
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + EPI_XPOSE_BYTES + 1024;  // +1024 alignment
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
@@ -196,11 +197,12 @@ __device__ __forceinline__ void epilogue_generic_chunk(const KParams& p, const u
 // Fast-path epilogue for 32 columns of one row: v = act(acc*alpha*cs + cb (+R)) * gain -> 128-bit stores.
 template <int ACT, bool OUT_BF16, int RES>   // RES: 0 none, 1 bf16, 2 fp32
 __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint32_t (&r)[32], float alpha, const float* cs_s,
-                                                    const float* cb_s, int c0, int n_base, long d_off, long r_off) {
+                                                    const float* cb_s, int c0, int n_base, long d_base, int row0, long r_off,
+                                                    uint4* stg) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]) * alpha, cs_s[c0 + i], cb_s[c0 + i]);
-    if (RES == 1) {
+    if (RES == 1 && r_off >= 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -211,7 +213,7 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
             unpack_bf16x2(a.z, lo, hi); v[8 * j + 4] += lo; v[8 * j + 5] += hi;
             unpack_bf16x2(a.w, lo, hi); v[8 * j + 6] += lo; v[8 * j + 7] += hi;
         }
-    } else if (RES == 2) {
+    } else if (RES == 2 && r_off >= 0) {
         const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + r_off + n_base);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -223,37 +225,64 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
     }
+    // Row-per-thread registers -> 32 x 64 B smem tile (XOR-swizzled 16 B pieces) -> each store instruction writes
+    // eight 64 B row segments (full 32 B sectors) instead of 32 scattered 16 B pieces.
     const float gain = p.post_gain;
+    const int lane = threadIdx.x & 31;
+    const int sw_w = (lane >> 1) & 3;
+    const int pc = lane & 3;
     if (OUT_BF16) {
-        uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + n_base);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint4 o;
             o.x = pack_bf16x2(v[8 * j + 0] * gain, v[8 * j + 1] * gain); o.y = pack_bf16x2(v[8 * j + 2] * gain, v[8 * j + 3] * gain);
             o.z = pack_bf16x2(v[8 * j + 4] * gain, v[8 * j + 5] * gain); o.w = pack_bf16x2(v[8 * j + 6] * gain, v[8 * j + 7] * gain);
-            dp[j] = o;
+            stg[lane * 4 + (j ^ sw_w)] = o;
         }
-    } else {
-        float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.D) + d_off + n_base);
+        __syncwarp();
+        __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.D) + d_base + n_base + pc * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j] * gain, v[4 * j + 1] * gain, v[4 * j + 2] * gain, v[4 * j + 3] * gain);
+        for (int i = 0; i < 4; ++i) {
+            const int rl = (lane >> 2) + 8 * i;
+            const uint4 val = stg[rl * 4 + (pc ^ ((rl >> 1) & 3))];
+            if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val;
+        }
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 16 * h + 4 * j;
+                stg[lane * 4 + (j ^ sw_w)] = make_uint4(__float_as_uint(v[b] * gain), __float_as_uint(v[b + 1] * gain),
+                                                         __float_as_uint(v[b + 2] * gain), __float_as_uint(v[b + 3] * gain));
+            }
+            __syncwarp();
+            float* dbase = reinterpret_cast<float*>(p.D) + d_base + n_base + 16 * h + pc * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = (lane >> 2) + 8 * i;
+                const uint4 val = stg[rl * 4 + (pc ^ ((rl >> 1) & 3))];
+                if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val;
+            }
+            __syncwarp();
+        }
     }
 }
 
 template <int ACT, bool OUT_BF16, int RES>
 __device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile& tl, uint32_t taddr, int col_begin, int col_end,
                                                    bool row_ok, float alpha, const float* cs_s, const float* cb_s,
-                                                   long d_off, long r_off, long c_off) {
+                                                   long d_off, long r_off, long c_off, long d_base, int row0, uint4* stg) {
     for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         const int n_base = tl.n0 + c0;
         if (n_base >= p.N) break;                       // warp-uniform
         uint32_t r[32];
         tmem_ld_x32(taddr + c0, r);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        if (n_base + 32 <= p.N) {
-            epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, r, alpha, cs_s, cb_s, c0, n_base, d_off, r_off);
-        } else {                                        // ragged last chunk of the matrix: scalar path
+        if (n_base + 32 <= p.N) {                       // whole warp takes this branch together (transposed stores)
+            epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, r, alpha, cs_s, cb_s, c0, n_base, d_base, row0, row_ok ? r_off : -1, stg);
+        } else if (row_ok) {                            // ragged last chunk of the matrix: scalar path
             uint32_t h[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) h[i] = r[i];
@@ -459,10 +488,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const long d_off = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2 + (long)row * p.ldd;
             const long r_off = (long)tl.b1 * p.r_sb1 + (long)tl.b2 * p.r_sb2 + (long)row * p.ldr;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
+            const long d_base = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2;
+            const int row0 = tl.m0 + q * 32;
+            uint4* stg = reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES) + e * 128;
             if (p.softmax) {
                 if (half == 0) epilogue_softmax_tile(p, tl, taddr, row_ok, row, alpha, cs_s, d_off);
             } else if (p.fast) {
-#define LD_EPI(ACT, BF, RES) epilogue_fast_tile<ACT, BF, RES>(p, tl, taddr, col_begin, col_end, row_ok, alpha, cs_s, cb_s, d_off, r_off, c_off)
+#define LD_EPI(ACT, BF, RES) epilogue_fast_tile<ACT, BF, RES>(p, tl, taddr, col_begin, col_end, row_ok, alpha, cs_s, cb_s, d_off, r_off, c_off, d_base, row0, stg)
 #define LD_EPI_ACT(BF, RES)                                           \
                 switch (p.act) {                                      \
                     case LD_ACT_RELU:    LD_EPI(LD_ACT_RELU, BF, RES); break;    \

@@ -121,3 +121,36 @@ def test_gemm_splitk_accumulate():
     k.gemm(M, N, K, k.Op(At, M, mn=True), k.Op(Bt, N, mn=True), k.Out(D2, N), accumulate=1)
     torch.cuda.synchronize()
     _check(D2, base + At.float().t() @ Bt.float(), what="accumulate=1")
+
+
+@pytest.mark.parametrize("Lq,Lk,d,H,mask_inf,causal", [(256, 256, 192, 4, False, False), (256, 256, 192, 4, False, True),
+                                                      (64, 64, 32, 8, True, False), (10, 10, 32, 8, True, False),
+                                                      (9, 64, 32, 8, True, False), (200, 136, 64, 2, False, True)])
+def test_gemm_fused_softmax_epilogue(Lq, Lk, d, H, mask_inf, causal):
+    """QK^T with scale + key/causal mask + softmax + bf16 cast fused into the TMEM drain."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(Lq * 3 + Lk)
+    Bn = 3
+    q = _rand((Bn * Lq, H * d), g, 0.7)
+    kk = _rand((Bn * Lk, H * d), g, 0.7)
+    km = torch.zeros((Bn, Lk), dtype=torch.uint8, device="cuda")
+    km[0, Lk // 2:] = 1
+    km[2, -1] = 1
+    Lkp = (Lk + 7) // 8 * 8
+    P = torch.full((Bn * H, Lq, Lkp), 7.0, dtype=torch.bfloat16, device="cuda")
+    scale = 1.0 / d ** 0.5
+    k.gemm(Lq, Lk, d, k.Op(q, H * d, sb1=Lq * H * d, sb2=d), k.Op(kk, H * d, sb1=Lk * H * d, sb2=d),
+           k.Out(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), nb1=Bn, nb2=H, alpha=scale,
+           softmax=dict(key_mask=km, mask_inf=mask_inf, causal=causal))
+    qf = q.float().view(Bn, Lq, H, d).permute(0, 2, 1, 3)
+    kf = kk.float().view(Bn, Lk, H, d).permute(0, 2, 1, 3)
+    s = qf @ kf.transpose(-1, -2) * scale
+    neg = float("-inf") if mask_inf else -10000.0
+    s = s + torch.zeros_like(s).masked_fill(km.bool()[:, None, None, :], neg)
+    if causal:
+        s = s + torch.zeros_like(s).masked_fill(torch.ones(Lq, Lk, device="cuda").triu(1).bool()[None, None], neg)
+    ref = torch.softmax(s, -1).reshape(Bn * H, Lq, Lk)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(P[:, :, :Lk].float(), ref, atol=4e-3, rtol=2e-2)
+    if Lkp > Lk:
+        assert float(P[:, :, Lk:].abs().max()) == 0.0
