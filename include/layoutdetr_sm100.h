@@ -101,6 +101,100 @@ typedef struct ld_gemm_desc {
 
 int ld_gemm_bf16(const ld_gemm_desc* desc, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * bias_act — replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:33-97, kernel bias_act.cu:24-148).
+ * y = clamp(act(x + b[(i / stepB) % sizeB]) * gain); grad = 1 / 2 evaluate the first / second order
+ * gradient forms from (xref, yref, dy) exactly like the reference kernel.  act = reference cuda_idx 1..9
+ * (linear, relu, lrelu, tanh, sigmoid, elu, selu, softplus, swish).  dtype: LD_F32 / LD_BF16.  Any pointer
+ * except x, y may be NULL.  clamp < 0 disables clamping.
+ * ------------------------------------------------------------------------------------------ */
+int ld_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                int dtype, int grad, int act, float alpha, float gain, float clamp,
+                int64_t sizeX, int sizeB, int64_t stepB, void* stream);
+
+/* upfirdn2d — replaces upfirdn2d_plugin.upfirdn2d (torch_utils/ops/upfirdn2d.cpp:17-105, kernels upfirdn2d.cu:30,98).
+ * Zero-insert upsample -> pad/crop -> FIR (fp32 filter [fh, fw], <= 32x32) -> decimate, strided 4-D tensors
+ * (element strides for N, C, H, W; NCHW or channels-last), output size must be
+ * (in*up + pad0 + pad1 - f + down) / down per axis. */
+int ld_upfirdn2d(const void* x, void* y, int dtype, const float* f, int fh, int fw,
+                 int N, int C, int inH, int inW, int outH, int outW,
+                 const int64_t* x_strides, const int64_t* y_strides,
+                 int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                 int flip_filter, float gain, void* stream);
+
+/* fma — replaces torch_utils/ops/fma.py:16 (a * b + c); b / c broadcast through element strides (0 on broadcast
+ * dims) in the index space of the contiguous 4-D tensor a. */
+int ld_fma_f32(const float* a, const float* b, const float* c, float* y, const int64_t* a_shape,
+               const int64_t* b_strides, const int64_t* c_strides, void* stream);
+
+/* LayerNorm (nn.LayerNorm: training/med.py:63,233,318,513; training/detr_transformer.py:191-192,252-254,41).
+ * rows x C, C % 128 == 0 and C <= 1024.  fwd optionally saves mean / rstd; bwd accumulates dgamma / dbeta with
+ * atomics into caller buffers (the parameters' .grad) and writes dx as bf16 and/or fp32. */
+int ld_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta,
+                     void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
+                     int rows, int C, float eps, void* stream);
+int ld_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                     const float* mean, const float* rstd, const float* gamma,
+                     void* dx_bf16, float* dx_f32, int64_t lddx, float* dgamma, float* dbeta,
+                     int rows, int C, void* stream);
+
+/* BERT embeddings: y = LayerNorm(word[ids[r]] + pos[r % T]) (training/med.py:74-97) and the scatter-add of its
+ * gradient into the (fp32) embedding tables; rows with ids == pad_id get no word gradient (padding_idx). */
+int ld_embed_ln_fwd(const int64_t* ids, const float* word, const float* pos, const float* gamma, const float* beta,
+                    void* y_bf16, float* pre_f32, float* mean, float* rstd, int rows, int T, int C, float eps, void* stream);
+int ld_embed_bwd(const int64_t* ids, const float* dpre, float* dword, float* dpos, int64_t rows, int T, int C,
+                 int64_t pad_id, void* stream);
+
+/* Masked row softmax for score matrices too wide for the fused GEMM epilogue (keys > 256), and its backward
+ * dS = P * (dP - sum(dP * P)) * scale.  Mask semantics as in ld_gemm_desc.softmax. */
+int ld_softmax_fwd(const float* S, int64_t lds, int64_t s_sb, void* P_bf16, int64_t ldp, int64_t p_sb,
+                   int nb1, int nb2, int rows, int cols, float scale, const uint8_t* key_mask, int mask_inf, int causal,
+                   void* stream);
+int ld_softmax_bwd(const void* P_bf16, int64_t ldp, int64_t p_sb, const float* dP, int64_t lddp, int64_t dp_sb,
+                   void* dS_bf16, int64_t ldds, int64_t ds_sb, int nb, int rows, int cols, float scale, void* stream);
+
+/* Row-wise softmax cross-entropy with label smoothing / ignore_index, loss and d(loss)/d(logits) in one pass
+ * (CrossEntropyLoss(label_smoothing=0.1) training/med.py:917-918; F.cross_entropy training/networks_detr.py:185,344,
+ * training/loss.py:105,178,189).  dlogits may alias logits. */
+int ld_cross_entropy(const void* logits, int dtype, int64_t ld_, const int64_t* labels, float* loss_rows,
+                     void* dlogits, int g_dtype, int64_t ldg, int64_t rows, int V, float label_smoothing,
+                     int64_t ignore_index, float grad_scale, void* stream);
+
+/* Convolution support around the GEMM (channels-last bf16): patch gather / its gather-form adjoint, the ResNet stem
+ * max-pool (torchvision resnet50 via training/detr_backbone.py:105) and NCHW <-> NHWC conversion. */
+int ld_im2col_nhwc(const void* x_bf16, void* cols_bf16, int B, int H, int W, int C, int Ho, int Wo,
+                   int KH, int KW, int stride, int pad, int Kp, void* stream);
+int ld_col2im_nhwc(const void* cols_bf16, void* dx_bf16, int B, int H, int W, int C, int Ho, int Wo,
+                   int KH, int KW, int stride, int pad, int Kp, void* stream);
+int ld_maxpool3s2_fwd(const void* x_bf16, void* y_bf16, uint8_t* argmax, int B, int H, int W, int C, void* stream);
+int ld_maxpool3s2_bwd(const void* dy_bf16, const uint8_t* argmax, void* dx_bf16, int B, int H, int W, int C, void* stream);
+int ld_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C, int64_t HW, int direction, void* stream);
+
+/* StyleGAN2 modulated-conv pieces on channels-last activations (training/networks_stylegan2.py:30-75, 307-325):
+ * per-sample channel scaling, demodulation + bias + leaky-ReLU (fwd / bwd) and the style-gradient reduction. */
+int ld_scale_channels(const void* x, int x_dtype, const float* s, void* y, int y_dtype, int64_t n, int64_t per_sample, int C, void* stream);
+int ld_demod_bias_act_fwd(const void* x, int x_dtype, const float* d, const float* bias, void* y_bf16,
+                          int B, int64_t pixels, int C, int act, float gain, void* stream);
+int ld_demod_bias_act_bwd(const void* dy_bf16, const void* y_bf16, const void* x, int x_dtype, const float* d,
+                          void* dx_bf16, float* dd, float* dbias, int B, int64_t pixels, int C, int act, float gain, void* stream);
+int ld_channel_dot(const void* a, int a_dtype, const void* g_bf16, float* out, int B, int64_t pixels, int C, void* stream);
+
+/* Small elementwise helpers used between GEMMs. */
+int ld_cast_pad(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,
+                int64_t rows, int cols_src, int cols_dst, void* stream);
+int ld_axpby_bcast(const void* a, int a_dtype, const void* b, int b_dtype, void* out, int out_dtype,
+                   int64_t n, int64_t period, float alpha, float beta, void* stream);
+int ld_act_fwd_bf16(const void* x, void* y, int64_t n, int act, float gain, void* stream);
+int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, void* dx, int dx_dtype,
+               int64_t n, int act, float gain, void* stream);
+int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t rows, int cols, void* stream);
+
+/* Optimizer step over flat storage (training/training_loop.py:303-328): nan_to_num + Adam + bf16 shadow refresh in one
+ * pass, and the generator EMA.  n % 4 == 0, 16-byte aligned pointers; m may be NULL when beta1 == 0. */
+int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int step, float grad_scale, void* stream);
+int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,35 @@
+"""CPU: with the overlay first on sys.path, `training.networks_detr` / `torch_utils.ops.*` resolve to the sm_100a
+implementations while untouched modules still come from the reference checkout (only where it exists)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("LAYOUTDETR_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "training")), reason="reference checkout not present on this box")
+def test_overlay_resolution():
+    code = r'''
+import sys, types
+for n in ("seaborn", "skimage", "skimage.transform", "pytorch_fid", "pytorch_fid.fid_score"):
+    m = types.ModuleType(n); sys.modules[n] = m
+sys.modules["pytorch_fid.fid_score"].calculate_frechet_distance = None
+import training.networks_detr as nd, torch_utils.ops.bias_act as ba, torch_utils.ops.upfirdn2d as uf
+import torch_utils.ops.conv2d_gradfix as cg, torch_utils.misc as misc, dnnlib
+assert nd.Generator.__module__ == "layoutdetr_b200.training.networks_detr", nd.Generator.__module__
+assert "layoutdetr_b200" in ba.bias_act.__module__ and "layoutdetr_b200" in uf.upfirdn2d.__module__
+assert hasattr(cg, "no_weight_gradients") and misc.__file__.startswith(%r) and dnnlib.__file__.startswith(%r)
+print("OVERLAY_OK")
+''' % (REF, REF)
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(code)
+        probe = f.name
+    env = dict(os.environ, LAYOUTDETR_REFERENCE=REF, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "layoutdetr_b200.dropin.run", probe], env=env, capture_output=True, text=True,
+                       cwd=ROOT, timeout=300)
+    os.unlink(probe)
+    assert "OVERLAY_OK" in r.stdout, r.stdout + r.stderr
