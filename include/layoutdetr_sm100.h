@@ -195,6 +195,13 @@ int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  float eps, int step, float grad_scale, void* stream);
 int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float beta, void* stream);
 
+/* Batched Hungarian matching — scipy.optimize.linear_sum_assignment(cost, maximize) as called by
+ * metrics/metric_layoutnet.py:111,125,240 (compute_maximum_iou*, compute_maximum_docsim_for_layout).  fp64 cost
+ * [problems, nr, nc] with 1 <= nr, nc <= 16; rows_out / cols_out [problems, min(nr, nc)] in scipy's order; status
+ * 0 ok, -1 infeasible, -2 NaN / -inf entry.  Assignment is bit-identical to scipy (same scan order and tie-breaking). */
+int ld_lsap(const double* cost, int nr, int nc, int maximize, int64_t problems, int64_t* rows_out, int64_t* cols_out,
+            int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,3 +422,21 @@ def adam_flat(p, g, m, v, p16, lr, beta1, beta2, eps, step, grad_scale=1.0):
 def ema_flat(p_ema, p, p_ema16, beta):
     _cuda(p_ema, p)
     check(lib().ld_ema_flat(_p(p_ema), _p(p), _p(p_ema16), c_int64(p.numel()), c_float(beta), _stream()), "ld_ema_flat")
+
+
+def lsap(cost, maximize=False):
+    """Batched linear-sum-assignment on the GPU. cost: fp64 CUDA tensor [P, nr, nc] (or [nr, nc]);
+    returns (rows, cols) int64 [P, min(nr, nc)] exactly as scipy.optimize.linear_sum_assignment orders them."""
+    _cuda(cost)
+    single = cost.ndim == 2
+    c = cost.reshape(-1, cost.shape[-2], cost.shape[-1]).to(torch.float64).contiguous()
+    P, nr, nc = c.shape
+    k = min(nr, nc)
+    rows = torch.empty((P, k), dtype=torch.int64, device=c.device)
+    cols = torch.empty((P, k), dtype=torch.int64, device=c.device)
+    status = torch.empty(P, dtype=torch.int32, device=c.device)
+    check(lib().ld_lsap(_p(c), c_int(nr), c_int(nc), c_int(1 if maximize else 0), c_int64(P), _p(rows), _p(cols), _p(status),
+                        _stream()), "ld_lsap")
+    if single:
+        return rows[0], cols[0], status[0]
+    return rows, cols, status
