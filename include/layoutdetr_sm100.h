@@ -187,6 +187,7 @@ int ld_axpby_bcast(const void* a, int a_dtype, const void* b, int b_dtype, void*
 int ld_act_fwd_bf16(const void* x, void* y, int64_t n, int act, float gain, void* stream);
 int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, void* dx, int dx_dtype,
                int64_t n, int act, float gain, void* stream);
+int ld_act_bwd_colscale(const void* dy, const void* ref, void* dx, void* dxs, const float* cs, int64_t n, int cols, int act, void* stream);
 int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t rows, int cols, void* stream);
 
 /* Optimizer step over flat storage (training/training_loop.py:303-328): nan_to_num + Adam + bf16 shadow refresh in one

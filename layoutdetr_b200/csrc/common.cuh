@@ -59,17 +59,19 @@ __device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) 
     lo = __low2float(h); hi = __high2float(h);
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, i.e. fp32-level): one rcp + one ex2 + 6 FMA instead of
-// erff's branchy polynomial — the GELU epilogue runs inside the GEMM's TMEM drain.
+// erf via Abramowitz-Stegun 7.1.28: erf(x) = 1 - (1 + a1 x + ... + a6 x^6)^-16 for x >= 0 (|abs err| < 3e-7, fp32-level):
+// 6 FMA + 4 squarings + ONE special-function op (rcp) and no branches — the GELU epilogue runs inside the GEMM's TMEM
+// drain, where the two MUFU ops of an exp-based formula were the bottleneck.
 __device__ __forceinline__ float fast_erf(float x) {
     const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float y = fmaf(1.061405429f, t, -1.453152027f);
-    y = fmaf(y, t, 1.421413741f);
-    y = fmaf(y, t, -0.284496736f);
-    y = fmaf(y, t, 0.254829592f);
-    y = 1.0f - y * t * __expf(-ax * ax);
-    return copysignf(y, x);
+    float t = fmaf(0.0000430638f, ax, 0.0002765672f);
+    t = fmaf(t, ax, 0.0001520143f);
+    t = fmaf(t, ax, 0.0092705272f);
+    t = fmaf(t, ax, 0.0422820123f);
+    t = fmaf(t, ax, 0.0705230784f);
+    t = fmaf(t, ax, 1.0f);
+    t *= t; t *= t; t *= t; t *= t;
+    return copysignf(1.0f - __fdividef(1.0f, t), x);
 }
 
 // exact (erf) GELU as used by BERT "gelu" (reference training/med.py:301, ACT2FN['gelu'])
@@ -197,6 +199,54 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) variants: two CTAs of a cluster cooperate on one 256-row MMA tile
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same smem offset in the LEADER CTA (rank 0)
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all prior MMAs of this thread retire) on the barrier at this smem offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 
 // Shared-memory matrix descriptor for tcgen05.mma (SWIZZLE_128B, bf16).
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4

@@ -184,6 +184,29 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
     }
 }
 
+// dx = dy * act'(ref) (bf16) and, in the same pass, dxs = dx * cs[col] — the conv + FrozenBN + (residual) + ReLU backward
+// needs both: dx feeds the residual branch, dxs the convolution (scale = w * rsqrt(var + eps), detr_backbone.py:55-65).
+__global__ void act_bwd_colscale_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ref, uint4* __restrict__ dx,
+                                        uint4* __restrict__ dxs, const float* __restrict__ cs, long n8, int cols, int act) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const uint4 g = dy[i]; const uint4 r = ref[i];
+        const int c0 = (int)((i * 8) % cols);
+        const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, rw[4] = {r.x, r.y, r.z, r.w};
+        uint32_t o[4], os[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float g0, g1, r0, r1;
+            unpack_bf16x2(gw[k], g0, g1); unpack_bf16x2(rw[k], r0, r1);
+            if (act == LD_ACT_RELU) { g0 = r0 > 0.f ? g0 : 0.f; g1 = r1 > 0.f ? g1 : 0.f; }
+            else if (act == LD_ACT_LRELU) { g0 = r0 > 0.f ? g0 : 0.2f * g0; g1 = r1 > 0.f ? g1 : 0.2f * g1; }
+            o[k] = pack_bf16x2(g0, g1);
+            os[k] = pack_bf16x2(g0 * cs[c0 + 2 * k], g1 * cs[c0 + 2 * k + 1]);
+        }
+        if (dx) dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        dxs[i] = make_uint4(os[0], os[1], os[2], os[3]);
+    }
+}
+
 // column sums of a [rows, cols] matrix accumulated into out[cols] (bias gradients)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long ld, float* __restrict__ out, long rows, int cols, int rows_per_block) {
@@ -307,6 +330,15 @@ int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, voi
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ref, (__nv_bfloat16*)dx, n, act, gain);
     ld::count_launch();
     LD_LAUNCH_CHECK("act_bwd");
+    return 0;
+}
+
+int ld_act_bwd_colscale(const void* dy, const void* ref, void* dx, void* dxs, const float* cs, int64_t n, int cols, int act, void* stream) {
+    LD_CHECK_ARG(dy && dxs && cs && n > 0 && cols > 0 && n % 8 == 0 && cols % 8 == 0, "act_bwd_colscale: bad argument");
+    LD_CHECK_ARG(act == LD_ACT_NONE || ref, "act_bwd_colscale: activation needs its output");
+    act_bwd_colscale_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)(ref ? ref : dy), (uint4*)dx, (uint4*)dxs, cs, n / 8, cols, act);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("act_bwd_colscale");
     return 0;
 }
 

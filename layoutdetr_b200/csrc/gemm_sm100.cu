@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "runtime.h"
 #include "../../include/layoutdetr_sm100.h"
+#include <cstdlib>
 
 namespace {
 
@@ -25,10 +26,13 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_STAGE_BYTES_MAX = 256 * BK * 2;     // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES_MAX;
+constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;    // 192 KB operand ring (1-SM: 4 x 48 KB, CTA-pair: 6 x 32 KB)
+constexpr int STAGES_2SM = 6;
+constexpr int STAGE_BYTES_2SM = 32768;              // per CTA: A 128 x 64 (16 KB) + B 128 x 64 (16 KB)
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 2 * 2 * 256 * 4;    // [acc stage][scale|bias][256] fp32
 constexpr int EPI_XPOSE_BYTES = 8 * 2048;           // per epilogue warp: 32 rows x 64 B transpose buffer
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + EPI_XPOSE_BYTES + 1024;  // +1024 alignment
+constexpr int SMEM_BYTES = PIPE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + EPI_XPOSE_BYTES + 1024;  // +1024 alignment
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
@@ -39,6 +43,7 @@ struct KParams {
     int act, accumulate, split_k, d_dtype, r_dtype, bn;
     int a_mn, b_mn;
     int m_tiles, n_tiles, kb_total, kb_per_split, total_tiles;
+    int tile_m;      // 128 (one CTA per tile) or 256 (CTA pair, cta_group::2)
     int vec_ok;
     int fast;        // compile-time specialised epilogue usable (aligned rows, store-only, no aux)
     float alpha, post_gain;
@@ -61,7 +66,7 @@ __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
     const int mt = t % p.m_tiles; t /= p.m_tiles;
     tl.b2 = t % p.nb2;
     tl.b1 = t / p.nb2;
-    tl.m0 = mt * BM;
+    tl.m0 = mt * p.tile_m;
     tl.n0 = nt * p.bn;
     tl.kb_begin = ks * p.kb_per_split;
     tl.kb_end = min(p.kb_total, tl.kb_begin + p.kb_per_split);
@@ -361,15 +366,20 @@ __device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Ti
     }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+template <bool TWO_SM>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p) {
+    constexpr int NSTAGE = TWO_SM ? STAGES_2SM : STAGES;
+    constexpr int SBYTES = TWO_SM ? STAGE_BYTES_2SM : STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar  = full_bar + STAGES;
-    uint64_t* tfull_bar  = empty_bar + STAGES;
+    uint64_t* full_bar   = reinterpret_cast<uint64_t*>(smem + PIPE_BYTES);
+    uint64_t* empty_bar  = full_bar + NSTAGE;
+    uint64_t* tfull_bar  = empty_bar + NSTAGE;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot  = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const uint32_t rank = TWO_SM ? cluster_ctarank() : 0u;        // 0 = leader (issues the MMAs)
+    const int unit = TWO_SM ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nunits = TWO_SM ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -379,16 +389,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TWO_SM ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (TWO_SM) { tmem_alloc_2sm(tmem_slot, TMEM_COLS); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (TWO_SM) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -396,39 +406,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = A_STAGE_BYTES + p.bn * BK * 2;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int b_rows = TWO_SM ? (p.bn >> 1) : p.bn;           // B rows this CTA stages per k-block
+            const uint32_t tx_bytes = (TWO_SM ? 2u : 1u) * (A_STAGE_BYTES + b_rows * BK * 2);
+            for (int t = unit; t < p.total_tiles; t += nunits) {
                 const Tile tl = decode_tile(p, t);
+                const int am0 = tl.m0 + (int)rank * BM;
+                const int bn0 = tl.n0 + (int)rank * b_rows;
                 for (int kb = tl.kb_begin; kb < tl.kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                    uint8_t* sa = smem + stage * SBYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     const int k0 = kb * BK;
                     if (!p.a_mn) {
-                        tma_load_4d(sa, &tmA, &full_bar[stage], k0, tl.m0, tl.b2, tl.b1);
+                        if (TWO_SM) tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, am0, tl.b2, tl.b1);
+                        else tma_load_4d(sa, &tmA, &full_bar[stage], k0, am0, tl.b2, tl.b1);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], tl.m0 + 64 * j, k0, tl.b2, tl.b1);
+                        for (int j = 0; j < BM / 64; ++j) {
+                            if (TWO_SM) tma_load_4d_2sm(sa + j * 8192, &tmA, &full_bar[stage], am0 + 64 * j, k0, tl.b2, tl.b1);
+                            else tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], am0 + 64 * j, k0, tl.b2, tl.b1);
+                        }
                     }
                     if (!p.b_mn) {
-                        tma_load_4d(sb, &tmB, &full_bar[stage], k0, tl.n0, tl.b2, tl.b1);
+                        if (TWO_SM) tma_load_4d_2sm(sb, &tmB, &full_bar[stage], k0, bn0, tl.b2, tl.b1);
+                        else tma_load_4d(sb, &tmB, &full_bar[stage], k0, bn0, tl.b2, tl.b1);
                     } else {
-                        for (int j = 0; j < p.bn / 64; ++j)
-                            tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], tl.n0 + 64 * j, k0, tl.b2, tl.b1);
+                        for (int j = 0; j < b_rows / 64; ++j) {
+                            if (TWO_SM) tma_load_4d_2sm(sb + j * 8192, &tmB, &full_bar[stage], bn0 + 64 * j, k0, tl.b2, tl.b1);
+                            else tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], bn0 + 64 * j, k0, tl.b2, tl.b1);
+                        }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            const uint32_t idesc = make_idesc_bf16(BM, p.bn, p.a_mn, p.b_mn);
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const uint32_t idesc = make_idesc_bf16(TWO_SM ? 256 : BM, p.bn, p.a_mn, p.b_mn);
+            for (int t = unit; t < p.total_tiles; t += nunits) {
                 const Tile tl = decode_tile(p, t);
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
@@ -436,7 +455,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = tl.kb_begin; kb < tl.kb_end; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * SBYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -446,12 +465,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                    : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t db = p.b_mn ? make_smem_desc(sb + k * 2048, 8192, 1024)
                                                    : make_smem_desc(sb + k * 32, 16, 1024);
-                        umma_bf16_ss(tmem_d, da, db, idesc, (kb > tl.kb_begin || k > 0) ? 1u : 0u);
+                        const uint32_t acc = (kb > tl.kb_begin || k > 0) ? 1u : 0u;
+                        if (TWO_SM) umma_bf16_ss_2sm(tmem_d, da, db, idesc, acc);
+                        else umma_bf16_ss(tmem_d, da, db, idesc, acc);
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem stage once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+                    if (TWO_SM) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps of both CTAs
+                if (TWO_SM) umma_commit_2sm(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
                 as ^= 1; if (as == 0) aphase ^= 1;
             }
         }
@@ -461,12 +484,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = e & 3;                          // TMEM lane quadrant of this warp (hardware: warp_id % 4)
         const int half = e >> 2;                      // which half of the tile's columns
         const int et = threadIdx.x - 128;             // 0..255 within the epilogue group
-        float* epi_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
+        float* epi_s = reinterpret_cast<float*>(smem + PIPE_BYTES + BAR_BYTES);
         int as = 0; uint32_t aphase = 0;
         const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
         const int col_begin = half * (p.bn >> 1), col_end = col_begin + (p.bn >> 1);
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const Tile tl = decode_tile(p, t);
+        for (int t = unit; t < p.total_tiles; t += nunits) {
+            Tile tl = decode_tile(p, t);
+            tl.m0 += (int)rank * BM;                  // this CTA's 128 rows of the (pair) tile
             const long c_off = (long)tl.b1 * p.col_sb1 + (long)tl.b2 * p.col_sb2;
             float* cs_s = epi_s + as * 512;
             float* cb_s = cs_s + 256;
@@ -490,7 +514,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
             const long d_base = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2;
             const int row0 = tl.m0 + q * 32;
-            uint4* stg = reinterpret_cast<uint4*>(smem + STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES) + e * 128;
+            uint4* stg = reinterpret_cast<uint4*>(smem + PIPE_BYTES + BAR_BYTES + EPI_STAGE_BYTES) + e * 128;
             if (p.softmax) {
                 if (half == 0) epilogue_softmax_tile(p, tl, taddr, row_ok, row, alpha, cs_s, d_off);
             } else if (p.fast) {
@@ -524,14 +548,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) { if (TWO_SM) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]); }
             as ^= 1; if (as == 0) aphase ^= 1;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (TWO_SM) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) { if (TWO_SM) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    gemm_body<false>(tmA, tmB, p);
+}
+
+// CTA-pair variant: 256 x 256 tile per cluster of two CTAs (tcgen05.mma.cta_group::2); each CTA stages its own 128 rows of
+// A and 128 of the 256 B rows, halving the L2->smem operand traffic per MMA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+    gemm_body<true>(tmA, tmB, p);
 }
 
 int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K, int nb1, int nb2, int box_rows) {
@@ -588,10 +624,17 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     p.softmax = d->softmax ? 1 : 0; p.causal = d->causal ? 1 : 0; p.mask_value = d->mask_value; p.key_mask = d->key_mask;
 
     const int sms = sm_count();
-    p.m_tiles = ceil_div(p.M, BM);
+    // CTA pairs (cta_group::2) for problems with enough 256 x 256 tiles to fill the chip; LD_GEMM_2SM=0 disables
+    static const int env_2sm = [] { const char* e = getenv("LD_GEMM_2SM"); return e ? atoi(e) : 1; }();
+    const long nb_ = (long)d->nb1 * d->nb2;
+    const bool two_sm = env_2sm && d->block_n != 128 && d->N > 128 && d->M >= 256 && !d->softmax &&
+                        nb_ * ceil_div(d->M, 256) * ceil_div(d->N, 256) * d->split_k >= (sms / 2);
+    p.tile_m = two_sm ? 256 : BM;
+    p.m_tiles = ceil_div(p.M, p.tile_m);
     const long nb = (long)p.nb1 * p.nb2;
     int bn = d->block_n;
     if (d->softmax) bn = d->N > 128 ? 256 : 128;      // the whole key axis in one tile
+    if (two_sm) bn = 256;
     if (bn == 0) {
         const long tiles256 = nb * p.m_tiles * ceil_div(p.N, 256) * p.split_k;
         bn = (p.N > 128 && tiles256 >= sms) ? 256 : 128;
@@ -623,17 +666,24 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     alignas(64) CUtensorMap tmA, tmB;
     int e = make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
     if (e) return e;
-    e = make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, bn);
+    e = make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, two_sm ? bn / 2 : bn);
     if (e) return e;
 
     static bool attr_set = false;
     if (!attr_set) {
-        int s = cuda_status(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "gemm: set smem attr");
-        if (s) return s;
+        int s1 = cuda_status(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "gemm: set smem attr");
+        if (s1) return s1;
+        s1 = cuda_status(cudaFuncSetAttribute(gemm_bf16_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "gemm: set smem attr (2sm)");
+        if (s1) return s1;
         attr_set = true;
     }
-    const int grid = (int)(total < sms ? total : sms);
-    gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    if (two_sm) {
+        const int pairs = (int)(total < sms / 2 ? total : sms / 2);
+        gemm_bf16_2sm_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    } else {
+        const int grid = (int)(total < sms ? total : sms);
+        gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    }
     count_launch();
     LD_LAUNCH_CHECK("gemm launch");
     return 0;

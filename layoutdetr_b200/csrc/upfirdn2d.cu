@@ -57,6 +57,48 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(UpfirdnArgs p) {
         y[n * p.ysn + c * p.ysc + oy * p.ysh + ox * p.ysw] = (T)(acc * p.gain);
     }
 }
+
+// Channels-last bf16 fast path (C % 8 == 0): one thread = one output pixel x 8 channels, 128-bit loads/stores along C.
+__global__ void __launch_bounds__(256) upfirdn2d_nhwc_bf16x8_kernel(UpfirdnArgs p) {
+    __shared__ float sf[32 * 32];
+    for (int i = threadIdx.x; i < p.fh * p.fw; i += blockDim.x) {
+        const int fy = i / p.fw, fx = i - fy * p.fw;
+        sf[i] = (p.flip ? p.f[i] : p.f[(p.fh - 1 - fy) * p.fw + (p.fw - 1 - fx)]) * p.gain;
+    }
+    __syncthreads();
+    const __nv_bfloat16* x = (const __nv_bfloat16*)p.x; __nv_bfloat16* y = (__nv_bfloat16*)p.y;
+    const int C8 = p.C >> 3;
+    const long total = (long)p.N * p.outH * p.outW * C8;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8); long t = i / C8;
+        const int ox = (int)(t % p.outW); t /= p.outW;
+        const int oy = (int)(t % p.outH); const int n = (int)(t / p.outH);
+        const int by = oy * p.downy - p.pady0, bx = ox * p.downx - p.padx0;
+        const int fy0 = ((-by) % p.upy + p.upy) % p.upy;
+        const int fx0 = ((-bx) % p.upx + p.upx) % p.upx;
+        const __nv_bfloat16* xb = x + n * p.xsn + c8 * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int fy = fy0; fy < p.fh; fy += p.upy) {
+            const int iy = (by + fy) / p.upy;
+            if (by + fy < 0 || iy >= p.inH) continue;
+            for (int fx = fx0; fx < p.fw; fx += p.upx) {
+                const int ix = (bx + fx) / p.upx;
+                if (bx + fx < 0 || ix >= p.inW) continue;
+                const float w = sf[fy * p.fw + fx];
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + iy * p.xsh + ix * p.xsw));
+                float lo, hi;
+                unpack_bf16x2(v.x, lo, hi); acc[0] = fmaf(w, lo, acc[0]); acc[1] = fmaf(w, hi, acc[1]);
+                unpack_bf16x2(v.y, lo, hi); acc[2] = fmaf(w, lo, acc[2]); acc[3] = fmaf(w, hi, acc[3]);
+                unpack_bf16x2(v.z, lo, hi); acc[4] = fmaf(w, lo, acc[4]); acc[5] = fmaf(w, hi, acc[5]);
+                unpack_bf16x2(v.w, lo, hi); acc[6] = fmaf(w, lo, acc[6]); acc[7] = fmaf(w, hi, acc[7]);
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(y + n * p.ysn + oy * p.ysh + ox * p.ysw + c8 * 8) = o;
+    }
+}
 }  // namespace
 
 extern "C" int ld_upfirdn2d(const void* x, void* y, int dtype, const float* f, int fh, int fw,
@@ -82,7 +124,15 @@ extern "C" int ld_upfirdn2d(const void* x, void* y, int dtype, const float* f, i
     p.channels_last = (y_strides[1] == 1 && C > 1) ? 1 : 0;
     const long total = (long)N * C * outH * outW;
     const int grid = (int)std::max<long>(1, std::min<long>((total + 255) / 256, (long)ld::sm_count() * 16));
-    if (dtype == LD_F32) upfirdn2d_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    const bool vec8 = dtype == LD_BF16 && p.channels_last && x_strides[1] == 1 && C % 8 == 0 &&
+                      (((uintptr_t)x | (uintptr_t)y) & 15) == 0 &&
+                      x_strides[0] % 8 == 0 && x_strides[2] % 8 == 0 && x_strides[3] % 8 == 0 &&
+                      y_strides[0] % 8 == 0 && y_strides[2] % 8 == 0 && y_strides[3] % 8 == 0;
+    if (vec8) {
+        const long tv = total / 8;
+        const int gv = (int)std::max<long>(1, std::min<long>((tv + 255) / 256, (long)ld::sm_count() * 16));
+        upfirdn2d_nhwc_bf16x8_kernel<<<gv, 256, 0, (cudaStream_t)stream>>>(p);
+    } else if (dtype == LD_F32) upfirdn2d_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     else upfirdn2d_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     ld::count_launch();
     LD_LAUNCH_CHECK("upfirdn2d");

@@ -493,13 +493,20 @@ class Conv2dFn(torch.autograd.Function):
         weight = ctx.weight
         Cout, Cin, KH, KW = weight.shape
         dy = dy.contiguous()
-        dpre = K.act_bwd(dy, out, ctx.act) if ctx.act != K.ACT_NONE else dy
-        dres = dpre if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        want_res = ctx.has_res and ctx.needs_input_grad[4]
+        if ctx.scale is not None and Cout % 8 == 0 and ctx.act in (K.ACT_NONE, K.ACT_RELU, K.ACT_LRELU):
+            # one pass: activation backward (for the residual branch) + FrozenBN scale (for the convolution)
+            dpre, dconv = K.act_bwd_colscale(dy, out, ctx.scale, ctx.act, want_dx=want_res and ctx.act != K.ACT_NONE)
+            if ctx.act == K.ACT_NONE:
+                dpre = dy
+        else:
+            dpre = K.act_bwd(dy, out, ctx.act) if ctx.act != K.ACT_NONE else dy
+            dconv = dpre
+            if ctx.scale is not None:
+                dconv = K.scale_channels(dpre, ctx.scale, torch.bfloat16, dpre.numel(), Cout)
+        dres = dpre if want_res else None
         if ctx.shift_param is not None and ctx.needs_input_grad[3]:
-            _bgrad(ctx.shift_param, 0, Cout, dpre)
-        dconv = dpre
-        if ctx.scale is not None:
-            dconv = K.scale_channels(dpre, ctx.scale, torch.bfloat16, dpre.numel(), Cout)
+            _bgrad(ctx.shift_param, 0, Cout, dpre if dpre is not None else dy)
         w16 = conv_weight_bf16(weight)
         dx = None
         if ctx.needs_input_grad[0]:

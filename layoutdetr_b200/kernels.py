@@ -286,6 +286,16 @@ def act_bwd(dy, ref, act, gain=1.0):
     return dx
 
 
+def act_bwd_colscale(dy, ref, cs, act, want_dx):
+    """(dx, dx * cs[col]) with dx = dy * act'(ref); bf16 [rows, cols], cols % 8 == 0."""
+    dy = dy.contiguous()
+    dxs = torch.empty_like(dy)
+    dx = torch.empty_like(dy) if want_dx else None
+    check(lib().ld_act_bwd_colscale(_p(dy), _p(ref), _p(dx), _p(dxs), _p(cs), c_int64(dy.numel()), c_int(dy.shape[1]), c_int(act),
+                                    _stream()), "ld_act_bwd_colscale")
+    return dx, dxs
+
+
 def act_fwd(x, act, gain=1.0):
     x = x.contiguous()
     y = torch.empty_like(x)

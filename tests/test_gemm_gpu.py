@@ -58,6 +58,36 @@ def test_gemm_epilogue(block_n):
         _check(aux, pre, tol=1e-2, what="aux act %d" % act)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_cta_pair_path_with_epilogue(a_mn, b_mn):
+    """Shapes with >= 74 tiles of 256x256 take the cta_group::2 kernel; check tails, bias/residual/activation, fp32 out."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(23)
+    M, N, K = 2304 + 72, 2560 + 40, 328
+    A, B = _rand((M, K), g, 0.5), _rand((N, K), g, 0.5)
+    bias = torch.randn(N, generator=g, device="cuda")
+    R = _rand((M, N), g)
+    At = A.t().contiguous() if a_mn else A
+    Bt = B.t().contiguous() if b_mn else B
+    pre = A.float() @ B.float().t() + bias + R.float()
+    D = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    k.gemm(M, N, K, k.Op(At, At.stride(0), mn=a_mn), k.Op(Bt, Bt.stride(0), mn=b_mn), k.Out(D, N), act=k.ACT_RELU,
+           R=k.Out(R, N), col_bias=bias)
+    torch.cuda.synchronize()
+    _check(D, torch.relu(pre), tol=1e-2, what="2sm relu")
+    D32 = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    k.gemm(M, N, K, k.Op(At, At.stride(0), mn=a_mn), k.Op(Bt, Bt.stride(0), mn=b_mn), k.Out(D32, N), R=k.Out(R, N), col_bias=bias)
+    torch.cuda.synchronize()
+    _check(D32, pre, tol=2e-3, what="2sm f32")
+    # batched: 8 x (512 x 512 x 192) -> 8*2*2 = 32 pair tiles < 74 stays single-CTA; 40 batches -> 160 pair tiles
+    nb = 40
+    Ab, Bb = _rand((nb * 512, 192), g), _rand((nb * 512, 192), g)
+    Db = torch.empty((nb, 512, 512), dtype=torch.float32, device="cuda")
+    k.gemm(512, 512, 192, k.Op(Ab, 192, sb1=512 * 192), k.Op(Bb, 192, sb1=512 * 192), k.Out(Db, 512, sb1=512 * 512), nb1=nb)
+    torch.cuda.synchronize()
+    _check(Db, Ab.float().view(nb, 512, 192) @ Bb.float().view(nb, 512, 192).transpose(1, 2), what="2sm batched")
+
+
 def test_gemm_batched_strided_attention_layout():
     """Q K^T and P V straight from a fused [B*T, 3*H*d] QKV buffer with two batch dims."""
     from layoutdetr_b200 import kernels as k
