@@ -196,6 +196,15 @@ int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  float eps, int step, float grad_scale, void* stream);
 int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float beta, void* stream);
 
+/* Fused multi-head attention forward (QK^T -> scale + mask -> softmax -> PV in one kernel, scores / probabilities stay
+ * on chip) for <= 256 keys and head_dim <= 192: BertSelfAttention.forward (training/med.py:146-228) and
+ * nn.MultiheadAttention as called by training/detr_transformer.py:208,273,277.  q / k / v: bf16 row-major [B*L, ld] buffers,
+ * head h in columns h*d .. h*d+d of the given base; o: bf16 [B*Lq, ldo]; p_out (optional, for the backward pass): bf16
+ * [B*H, Lq, ldp] normalised probabilities.  key_mask [B, Lk] (1 = masked) adds -10000 (mask_inf = 0) or -inf. */
+int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
+                     float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
+
 /* Batched Hungarian matching — scipy.optimize.linear_sum_assignment(cost, maximize) as called by
  * metrics/metric_layoutnet.py:111,125,240 (compute_maximum_iou*, compute_maximum_docsim_for_layout).  fp64 cost
  * [problems, nr, nc] with 1 <= nr, nc <= 16; rows_out / cols_out [problems, min(nr, nc)] in scipy's order; status

@@ -289,6 +289,9 @@ class EmbedLNFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+FUSED_ATTENTION = True       # False -> batched-GEMM attention (QK^T with fused softmax epilogue, then PV); used by tests
+
+
 class AttentionFn(torch.autograd.Function):
     """Multi-head attention core on projected buffers via batched tcgen05 GEMMs + masked softmax.
 
@@ -305,6 +308,18 @@ class AttentionFn(torch.autograd.Function):
         dev = q_t.device
         Lkp = E.pad8(Lk)
         ldq, ldk, ldv = q_t.stride(0), k_t.stride(0), v_t.stride(0)
+        need_grad = any(ctx.needs_input_grad)
+        ctx.dims = (q_off, k_off, v_off, B, H, Lq, Lk, d, scale)
+        if Lk <= 256 and d <= 192 and d % 8 == 0 and FUSED_ATTENTION:
+            # one kernel: QK^T -> mask/softmax -> PV; probabilities only go to HBM when the backward pass needs them
+            P = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev) if need_grad else None
+            if P is not None and Lkp != Lk:
+                P.zero_()
+            O = K.attention_fwd(q_t, q_off, k_t, k_off, v_t, v_off, B, H, Lq, Lk, d, scale, key_mask=key_mask,
+                                mask_inf=mask_inf, causal=causal, P_out=P)
+            if need_grad:
+                ctx.save_for_backward(q_t, k_t, v_t, P)
+            return O
         P = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
         if Lk <= 256:
             # scores never leave the SM: scale + mask + softmax + bf16 cast run in the GEMM's TMEM drain

@@ -183,6 +183,21 @@ def embed_bwd(ids, dpre, dword, dpos, T, pad_id):
                              _stream()), "ld_embed_bwd")
 
 
+def attention_fwd(q_t, q_off, k_t, k_off, v_t, v_off, B, H, Lq, Lk, d, scale, key_mask=None, mask_inf=False, causal=False,
+                  P_out=None):
+    """Fused attention forward. q_t/k_t/v_t: bf16 [B*L, ld] buffers (may alias), head h of q at columns q_off + h*d.
+    Returns O bf16 [B*Lq, H*d]; fills P_out [B*H, Lq, pad8(Lk)] with the probabilities if given."""
+    _cuda(q_t, k_t, v_t)
+    O = torch.empty((B * Lq, H * d), dtype=torch.bfloat16, device=q_t.device)
+    check(lib().ld_attention_fwd(c_void_p(q_t.data_ptr() + 2 * q_off), c_int64(q_t.stride(0)),
+                                 c_void_p(k_t.data_ptr() + 2 * k_off), c_int64(k_t.stride(0)),
+                                 c_void_p(v_t.data_ptr() + 2 * v_off), c_int64(v_t.stride(0)),
+                                 _p(O), c_int64(H * d), _p(P_out), c_int64(P_out.stride(1) if P_out is not None else 0),
+                                 c_int(B), c_int(H), c_int(Lq), c_int(Lk), c_int(d), c_float(scale), _p(key_mask),
+                                 c_int(1 if mask_inf else 0), c_int(1 if causal else 0), _stream()), "ld_attention_fwd")
+    return O
+
+
 def softmax_fwd(S, P, nb1, nb2, rows, cols, scale, key_mask=None, mask_inf=False, causal=False):
     """S fp32 [nb1*nb2, rows, ldS] -> P bf16 [nb1*nb2, rows, ldP] (both contiguous 3-D tensors)."""
     _cuda(S, P)
