@@ -153,7 +153,7 @@ def run_ours(args):
     from layoutdetr_b200 import _lib, kernels as K
     from layoutdetr_b200.synthetic import make_inputs
     from layoutdetr_b200.training import networks_detr as nd
-    from layoutdetr_b200.training.trainer import Trainer
+    from layoutdetr_b200.training.trainer import Trainer, GraphedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,15 +192,26 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    use_graph = bool(args.graph) and (world == 1 or os.environ.get("LD_GRAPH_MULTI", "0") == "1")
+    gs = GraphedStep(trainer) if use_graph else None
+    if gs is not None:
+        gs.run(host_batches[0], zs[0], zs[1])               # warm-up + capture of the whole iteration
+
     def step_resident():
-        trainer.iteration(resident, zs[0], zs[1])
+        if gs is not None:
+            gs.run_static()
+        else:
+            trainer.iteration(resident, zs[0], zs[1])
 
     def step_e2e(i):
         hb = host_batches[i % nb_host]
-        batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
         z1 = torch.randn((B, 9, 4), device=dev, generator=gz)
         z2 = torch.randn((B, 9, 4), device=dev, generator=gz)
-        last = trainer.iteration(batch, z1, z2)
+        if gs is not None:
+            last = gs.run(hb, z1, z2)                       # H2D into the graph's static inputs, host tokenisation, replay
+        else:
+            batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+            last = trainer.iteration(batch, z1, z2)
         vals = torch.stack([v.float().mean() for v in last["Gmain"].values()] + [v.float().mean() for v in last["Dmain"].values()])
         return vals.cpu()                                   # D2H read of the step's loss terms (synchronises)
 
@@ -229,6 +240,8 @@ def run_ours(args):
     sync_all()
     clocks = sampler.stop()
     launches = _lib.launch_count()
+    if gs is not None:                                      # replayed kernels are not counted by the library's host-side counter
+        launches = next(iter(gs.graphs.values()))["launches"] * args.steps
     ms_dev = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     t = torch.tensor([ms_dev], device=dev)
     if world > 1:
@@ -269,7 +282,8 @@ def run_ours(args):
                     config=dict(workload="bs16 256x256 synthetic, 8 of 9 slots, G+D fwd/bwd + Adam + EMA (BASELINE configs[1])",
                                 batch_per_gpu=B, global_batch=B * world, text_tokens=256, text_trim=bool(args.text_trim),
                                 text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
-                                dropout="off (deterministic eval-semantics kernels)", parallelism="dp%d" % world),
+                                dropout="off (deterministic eval-semantics kernels)", parallelism="dp%d" % world,
+                                launch="cuda graph replay of the captured iteration" if gs is not None else "eager (one launch per kernel)"),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
         print(json.dumps(line), flush=True)
@@ -286,6 +300,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU")
     ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
+    ap.add_argument("--graph", type=int, default=1, help="1: capture the iteration into a CUDA graph (single-GPU default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profile exactly one resident step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--steps-ref", type=int, default=1)

@@ -158,7 +158,8 @@ int ld_softmax_bwd(const void* P_bf16, int64_t ldp, int64_t p_sb, const float* d
  * training/loss.py:105,178,189).  dlogits may alias logits. */
 int ld_cross_entropy(const void* logits, int dtype, int64_t ld_, const int64_t* labels, float* loss_rows,
                      void* dlogits, int g_dtype, int64_t ldg, int64_t rows, int V, float label_smoothing,
-                     int64_t ignore_index, float grad_scale, void* stream);
+                     int64_t ignore_index, float grad_scale, const float* grad_scale_dev /* optional device scalar factor */,
+                     void* stream);
 
 /* Convolution support around the GEMM (channels-last bf16): patch gather / its gather-form adjoint, the ResNet stem
  * max-pool (torchvision resnet50 via training/detr_backbone.py:105) and NCHW <-> NHWC conversion. */
@@ -193,7 +194,9 @@ int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t r
 /* Optimizer step over flat storage (training/training_loop.py:303-328): nan_to_num + Adam + bf16 shadow refresh in one
  * pass, and the generator EMA.  n % 4 == 0, 16-byte aligned pointers; m may be NULL when beta1 == 0. */
 int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
-                 float eps, int step, float grad_scale, void* stream);
+                 float eps, int step, float grad_scale,
+                 const float* hyper_dev /* optional device {lr, 1-beta1^t, 1-beta2^t} overriding lr/step (CUDA-graph replay) */,
+                 void* stream);
 int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float beta, void* stream);
 
 /* Fused multi-head attention forward (QK^T -> scale + mask -> softmax -> PV in one kernel, scores / probabilities stay

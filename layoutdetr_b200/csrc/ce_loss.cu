@@ -32,8 +32,10 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
 template <typename T, typename TG>
 __global__ void __launch_bounds__(CE_THREADS)
 ce_kernel(const T* __restrict__ logits, long ld_, const int64_t* __restrict__ labels, float* __restrict__ loss_rows,
-          TG* __restrict__ dlogits, long ldg, int V, float eps, long ignore_index, float grad_scale) {
+          TG* __restrict__ dlogits, long ldg, int V, float eps, long ignore_index, float grad_scale,
+          const float* __restrict__ grad_scale_dev) {
     __shared__ float sh[CE_THREADS / 32];
+    if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);
     const long r = blockIdx.x;
     const T* x = logits + r * ld_;
     const long y = labels[r];
@@ -67,11 +69,11 @@ ce_kernel(const T* __restrict__ logits, long ld_, const int64_t* __restrict__ la
 
 extern "C" int ld_cross_entropy(const void* logits, int dtype, int64_t ld_, const int64_t* labels, float* loss_rows,
                                 void* dlogits, int g_dtype, int64_t ldg, int64_t rows, int V, float label_smoothing,
-                                int64_t ignore_index, float grad_scale, void* stream) {
+                                int64_t ignore_index, float grad_scale, const float* grad_scale_dev, void* stream) {
     LD_CHECK_ARG(logits && labels && rows > 0 && V > 0, "cross_entropy: bad argument");
     LD_CHECK_ARG(loss_rows || dlogits, "cross_entropy: nothing to compute");
     cudaStream_t st = (cudaStream_t)stream;
-#define CE(T, TG) ce_kernel<T, TG><<<(unsigned)rows, CE_THREADS, 0, st>>>((const T*)logits, ld_, labels, loss_rows, (TG*)dlogits, ldg, V, label_smoothing, ignore_index, grad_scale)
+#define CE(T, TG) ce_kernel<T, TG><<<(unsigned)rows, CE_THREADS, 0, st>>>((const T*)logits, ld_, labels, loss_rows, (TG*)dlogits, ldg, V, label_smoothing, ignore_index, grad_scale, grad_scale_dev)
     if (dtype == LD_F32 && g_dtype == LD_F32) CE(float, float);
     else if (dtype == LD_F32) CE(float, __nv_bfloat16);
     else if (g_dtype == LD_F32) CE(__nv_bfloat16, float);

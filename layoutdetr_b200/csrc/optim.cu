@@ -21,7 +21,9 @@ __device__ __forceinline__ float sanitize(float g) {
 
 __global__ void __launch_bounds__(256)
 adam_flat_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
-                 uint2* __restrict__ p16, long n4, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
+                 uint2* __restrict__ p16, long n4, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale,
+                 const float* __restrict__ hyper_dev) {
+    if (hyper_dev) { lr = __ldg(hyper_dev); bc1 = __ldg(hyper_dev + 1); bc2 = __ldg(hyper_dev + 2); }
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 pv = p[i];
         const float4 gv4 = g[i];
@@ -63,14 +65,14 @@ ema_flat_kernel(float4* __restrict__ p_ema, const float4* __restrict__ p, uint2*
 extern "C" {
 // n must be a multiple of 4 (flat storage is padded); all pointers 16-byte aligned.
 int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1, float beta2,
-                 float eps, int step, float grad_scale, void* stream) {
+                 float eps, int step, float grad_scale, const float* hyper_dev, void* stream) {
     LD_CHECK_ARG(p && g && v && n > 0 && n % 4 == 0 && step >= 1, "adam_flat: bad argument");
     LD_CHECK_ARG(beta1 == 0.f || m != nullptr, "adam_flat: beta1 != 0 needs the first-moment buffer");
     const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     const long n4 = n / 4;
     const int grid = (int)std::min<long>((n4 + 255) / 256, (long)ld::sm_count() * 8);
     adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16,
-                                                             n4, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+                                                             n4, lr, beta1, beta2, eps, bc1, bc2, grad_scale, hyper_dev);
     ld::count_launch();
     LD_LAUNCH_CHECK("adam_flat");
     return 0;

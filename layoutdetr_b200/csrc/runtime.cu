@@ -60,6 +60,10 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                         uint32_t box_inner, uint32_t box_outer) {
+    // cuTensorMapEncodeTiled is a driver entry point: it needs the primary context bound to THIS thread (autograd runs
+    // backward on worker threads that may not have issued a runtime call yet).
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point unavailable (driver too old / no GPU)"); return LD_ERR_DRIVER; }
     cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};

@@ -53,6 +53,13 @@ def _lookup(key, params):
 
 
 def _store(key, params, value):
+    # Refresh IN PLACE when a previous shadow of the same shape exists: the device address of a derived shadow must stay
+    # stable so that a captured CUDA graph (which bakes pointers) keeps reading the buffer a later refresh writes.
+    old = _shadow.get(key)
+    if old is not None and torch.is_tensor(old[3]) and old[3].shape == value.shape and old[3].dtype == value.dtype \
+            and old[3].device == value.device:
+        old[3].copy_(value)
+        value = old[3]
     _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
                     tuple(_generation.get(id(p), 0) for p in params), value)
     return value

@@ -29,6 +29,7 @@ class FlatParams:
         self.m = torch.zeros(total, dtype=torch.float32, device=dev) if (beta1 != 0.0 and with_grad) else None
         self.p16 = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.step = 0
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=dev)     # {lr, 1 - beta1^t, 1 - beta2^t} read by the kernel
         with torch.no_grad():
             for p, o in zip(self.params, offs):
                 n = p.numel()
@@ -47,9 +48,16 @@ class FlatParams:
             if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * o:
                 p.grad = self.g[o:o + p.numel()].view(p.shape)
 
-    def adam_step(self, lr, beta1, beta2, eps, grad_scale=1.0):
+    def set_hyper(self, lr, beta1, beta2):
+        """Advance the step counter and publish the step-dependent scalars on the device (outside any graph capture)."""
         self.step += 1
-        K.adam_flat(self.p, self.g, self.m, self.v, self.p16, lr, beta1, beta2, eps, self.step, grad_scale)
+        self.hyper.copy_(torch.tensor([lr, 1.0 - beta1 ** self.step, 1.0 - beta2 ** self.step], dtype=torch.float32))
+
+    def adam_step(self, lr, beta1, beta2, eps, grad_scale=1.0):
+        if not torch.cuda.is_current_stream_capturing():
+            self.set_hyper(lr, beta1, beta2)          # a captured graph re-reads `hyper`, refreshed by its owner before replay
+        K.adam_flat(self.p, self.g, self.m, self.v, self.p16, lr, beta1, beta2, eps, max(1, self.step), grad_scale,
+                    hyper_dev=self.hyper)
         E.bump_generation(self.params)
 
     def ema_from(self, src, beta):

@@ -395,7 +395,7 @@ class LMHeadCEFn(torch.autograd.Function):
     buffer that is overwritten in place by d(loss)/d(logits)."""
 
     @staticmethod
-    def forward(ctx, h, emb_weight, bias, labels, n_valid, smoothing):
+    def forward(ctx, h, emb_weight, bias, labels, inv_n_valid, smoothing):
         M, C = h.shape
         V = emb_weight.shape[0]
         Vp = E.pad8(V)
@@ -404,13 +404,14 @@ class LMHeadCEFn(torch.autograd.Function):
         logits = buf[:, :V]
         K.gemm(M, V, C, K.Op(h, h.stride(0)), K.Op(w16, w16.stride(0)), K.Out(buf, Vp), col_bias=bias.detach())
         need_grad = any(ctx.needs_input_grad)
-        inv = 1.0 / max(1, n_valid)
-        loss_rows = K.cross_entropy(logits, labels, smoothing, -100, True, logits if need_grad else None, grad_scale=inv)
+        # inv_n_valid: fp32 device scalar = 1 / #targets (device-side so a captured CUDA graph stays valid for any batch)
+        loss_rows = K.cross_entropy(logits, labels, smoothing, -100, True, logits if need_grad else None, grad_scale=1.0,
+                                    grad_scale_dev=inv_n_valid)
         ctx.emb_weight, ctx.bias = emb_weight, bias
         if need_grad:
             ctx.save_for_backward(h, buf)
         ctx.V = V
-        return loss_rows.sum() * inv
+        return loss_rows.sum() * inv_n_valid.reshape(())
 
     @staticmethod
     def backward(ctx, g):
@@ -433,8 +434,8 @@ class LMHeadCEFn(torch.autograd.Function):
         return dh, None, None, None, None, None
 
 
-def lm_head_ce(h, emb_weight, bias, labels, n_valid, smoothing=0.1):
-    return LMHeadCEFn.apply(h, emb_weight, bias, labels, n_valid, smoothing)
+def lm_head_ce(h, emb_weight, bias, labels, inv_n_valid, smoothing=0.1):
+    return LMHeadCEFn.apply(h, emb_weight, bias, labels, inv_n_valid, smoothing)
 
 
 class CrossEntropyFn(torch.autograd.Function):

@@ -213,7 +213,8 @@ def softmax_bwd(P, dP, dS, nb, rows, cols, scale):
                                c_int(nb), c_int(rows), c_int(cols), c_float(scale), _stream()), "ld_softmax_bwd")
 
 
-def cross_entropy(logits, labels, label_smoothing=0.0, ignore_index=-100, want_loss=True, dlogits=None, grad_scale=1.0):
+def cross_entropy(logits, labels, label_smoothing=0.0, ignore_index=-100, want_loss=True, dlogits=None, grad_scale=1.0,
+                  grad_scale_dev=None):
     _cuda(logits, labels)
     rows, V = logits.shape
     loss_rows = torch.empty(rows, dtype=torch.float32, device=logits.device) if want_loss else None
@@ -221,7 +222,7 @@ def cross_entropy(logits, labels, label_smoothing=0.0, ignore_index=-100, want_l
     ldg = dlogits.stride(0) if dlogits is not None else 0
     check(lib().ld_cross_entropy(_p(logits), c_int(dt(logits)), c_int64(logits.stride(0)), _p(labels), _p(loss_rows),
                                  _p(dlogits), c_int(g_dt), c_int64(ldg), c_int64(rows), c_int(V),
-                                 c_float(label_smoothing), c_int64(ignore_index), c_float(grad_scale), _stream()),
+                                 c_float(label_smoothing), c_int64(ignore_index), c_float(grad_scale), _p(grad_scale_dev), _stream()),
           "ld_cross_entropy")
     return loss_rows
 
@@ -437,11 +438,11 @@ def channel_dot(a, g, B, pixels, C):
     return out
 
 
-def adam_flat(p, g, m, v, p16, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_flat(p, g, m, v, p16, lr, beta1, beta2, eps, step, grad_scale=1.0, hyper_dev=None):
     """Fused nan_to_num + Adam + bf16-shadow refresh over flat fp32 storage (numel % 4 == 0)."""
     _cuda(p, g, v)
     check(lib().ld_adam_flat(_p(p), _p(g), _p(m), _p(v), _p(p16), c_int64(p.numel()), c_float(lr), c_float(beta1),
-                             c_float(beta2), c_float(eps), c_int(step), c_float(grad_scale), _stream()), "ld_adam_flat")
+                             c_float(beta2), c_float(eps), c_int(step), c_float(grad_scale), _p(hyper_dev), _stream()), "ld_adam_flat")
 
 
 def ema_flat(p_ema, p, p_ema16, beta):

@@ -272,7 +272,11 @@ class BertLMHeadModel(nn.Module):
         shifted = torch.full_like(labels, -100)
         shifted[:, :-1] = labels[:, 1:]
         if n_valid is None:
-            n_valid = int((shifted != -100).sum())
+            inv = 1.0 / (shifted != -100).sum().clamp(min=1).float().reshape(1)          # device-side, no sync
+        elif torch.is_tensor(n_valid):
+            inv = n_valid                                                                  # already 1 / count (device scalar)
+        else:
+            inv = torch.full((1,), 1.0 / max(1, int(n_valid)), dtype=torch.float32, device=h.device)
         loss = Fn.lm_head_ce(h, self.bert.embeddings.word_embeddings.weight, self.cls.predictions.bias,
-                             shifted.reshape(-1).contiguous(), n_valid, 0.1)
+                             shifted.reshape(-1).contiguous(), inv, 0.1)
         return types.SimpleNamespace(loss=loss)

@@ -104,8 +104,14 @@ class _TextFrontEnd:
                                  return_tensors="pt")
             ids, mask = enc.input_ids, enc.attention_mask
             text_len = torch.from_numpy(np.array([len(t) for t in flat], dtype=np.int64))
-            self._val = dict(ids=ids.to(device), mask=mask.to(device), ids_cpu=ids, mask_cpu=mask,
-                             text_len=text_len.to(device))
+            old = self._val
+            if old is not None and old["ids"].shape == ids.shape and old["ids"].device == torch.device(device):
+                # refresh in place: device addresses stay stable (a captured CUDA graph keeps reading these buffers)
+                old["ids"].copy_(ids); old["mask"].copy_(mask); old["text_len"].copy_(text_len)
+                old["ids_cpu"], old["mask_cpu"] = ids, mask
+            else:
+                self._val = dict(ids=ids.to(device), mask=mask.to(device), ids_cpu=ids, mask_cpu=mask,
+                                 text_len=text_len.to(device))
             self._key = key
         return self._val
 
@@ -162,6 +168,12 @@ def _encode_text(module, text, B, N):
     return enc.cls_features(ids, mask).contiguous()
 
 
+def lm_target_count(text, valid_idx_cpu, pad_id, trim=False):
+    """Number of next-token targets of the valid slots (host-side; what the LM loss is averaged over)."""
+    ids_cpu = text["ids_cpu"][valid_idx_cpu]
+    return int(((ids_cpu != pad_id)[:, 1:]).sum())
+
+
 def _decode_text_loss(module, text, valid_idx_dev, valid_idx_cpu, bos_id, pad_id):
     """Causal-LM reconstruction loss of the strings of the valid slots (reference :169-181 / :328-340).
     The decoder runs mode='text': `encoder_hidden_states` is never read (training/med.py:361)."""
@@ -177,7 +189,15 @@ def _decode_text_loss(module, text, valid_idx_dev, valid_idx_cpu, bos_id, pad_id
     # next-token targets: positions 1.. of every non-pad token
     ids_cpu = text["ids_cpu"][valid_idx_cpu][:, :ids.shape[1]]
     n_valid = int(((ids_cpu != pad_id)[:, 1:]).sum())
-    out = module.text_decoder(ids, attention_mask=mask, labels=labels, return_dict=True, mode="text", n_valid=n_valid)
+    # 1 / #targets lives in a persistent device scalar: under CUDA-graph capture it is NOT rewritten here (the owner of the
+    # graph refreshes it before every replay, see trainer.GraphedStep), so the captured kernels stay valid for any batch.
+    buf = module.__dict__.get("_inv_n_valid")
+    if buf is None or buf.device != ids.device:
+        buf = torch.zeros(1, dtype=torch.float32, device=ids.device)
+        module.__dict__["_inv_n_valid"] = buf
+    if not torch.cuda.is_current_stream_capturing():
+        buf.fill_(1.0 / max(1, n_valid))
+    out = module.text_decoder(ids, attention_mask=mask, labels=labels, return_dict=True, mode="text", n_valid=buf)
     return out.loss
 
 

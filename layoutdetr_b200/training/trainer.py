@@ -55,13 +55,109 @@ class Trainer:
         o = self.opt[name]
         flat.adam_step(o["lr"], o["beta1"], o["beta2"], o["eps"], grad_scale=scale)
 
-    def iteration(self, batch, z_g, z_d):
+    def iteration(self, batch, z_g, z_d, update_ema=True):
         self._phase("G", batch, z_g)
         self._phase("D", batch, z_d)
+        if update_ema:
+            self.update_ema()
+        return self.loss.last
+
+    def update_ema(self):
         ema_nimg = self.ema_kimg * 1000
         if self.ema_rampup is not None:
             ema_nimg = min(ema_nimg, self.cur_nimg * self.ema_rampup)
         ema_beta = 0.5 ** (self.batch_size / max(ema_nimg, 1e-8))
         self.flat_ema.ema_from(self.flat["G"], ema_beta)
         self.cur_nimg += self.batch_size
-        return self.loss.last
+
+
+class GraphedStep:
+    """The whole training iteration (Gmain + Dmain + Adam + EMA, ~6.5k kernel launches) captured once into a CUDA graph
+    and replayed: the step is otherwise CPU-launch-bound (Python + autograd dispatch ~25 us per kernel vs ~22 us of GPU
+    work per kernel on average).  Shapes and host-derived facts (which slots are valid, token padding width) are baked into
+    a graph, so graphs are keyed on them; everything data-dependent is read from static device buffers that `run` refreshes
+    before each replay: images, boxes, classes, z, token ids / masks / lengths and the LM-loss normalisers."""
+
+    def __init__(self, trainer):
+        self.tr = trainer
+        self.graphs = {}
+
+    def _key(self, host_batch):
+        pm = host_batch["padding_mask"]
+        flat_len = tuple(len(t) > 0 for row in host_batch["bbox_text"] for t in row)
+        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), flat_len[:0])
+
+    def _refresh_host_derived(self, st, host_mask):
+        """Tokenise (host) into the front-ends' persistent device buffers and refresh the LM-loss normalisers."""
+        import numpy as np
+        from . import networks_detr as nd
+        tr = self.tr
+        dev = tr.device
+        vidx_cpu = np.flatnonzero(~host_mask.numpy().astype(bool).reshape(-1))
+        for m in (tr.G, tr.D):
+            text = m._front()(st["bbox_text"], dev)
+            n = nd.lm_target_count(text, vidx_cpu, m.tokenizer.pad_token_id)
+            buf = m.__dict__.get("_inv_n_valid")
+            if buf is None:
+                buf = torch.zeros(1, dtype=torch.float32, device=dev)
+                m.__dict__["_inv_n_valid"] = buf
+            buf.fill_(1.0 / max(1, n))
+
+    def run_static(self):
+        """Replay the (single) captured graph on whatever the static input buffers currently hold (inputs resident in HBM)."""
+        tr = self.tr
+        ent = next(iter(self.graphs.values()))
+        for name in ("G", "D"):
+            o = tr.opt[name]
+            tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
+        ent["graph"].replay()
+        tr.update_ema()
+        return ent["out"]
+
+    def run(self, host_batch, z_g, z_d):
+        """host_batch: dict of (pinned) CPU tensors + `bbox_text`; z_g / z_d: device tensors.  Returns the loss-term dict
+        (static device tensors, overwritten by the next call)."""
+        tr = self.tr
+        key = self._key(host_batch)
+        ent = self.graphs.get(key)
+        if ent is None:
+            st = {k: (v.to(tr.device) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+            st["z_g"], st["z_d"] = z_g.clone(), z_d.clone()
+            self._refresh_host_derived(st, host_batch["padding_mask"])
+            # warm up on a side stream (allocator pools, lazy inits, shadow caches reach their steady state), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    tr.iteration(st, st["z_g"], st["z_d"])
+            for name in ("G", "D"):                              # the captured pass itself also counts as one optimizer step
+                o = tr.opt[name]
+                tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            from .. import _lib
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                out = tr.iteration(st, st["z_g"], st["z_d"], update_ema=False)
+                out = {ph: {k: v for k, v in terms.items()} for ph, terms in out.items()}
+            ent = dict(graph=g, static=st, out=out, launches=_lib.launch_count() - n0)
+            self.graphs[key] = ent
+            g.replay()                                           # capture does not execute: run the step once
+            tr.update_ema()
+            return ent["out"]
+        st = ent["static"]
+        for k, v in host_batch.items():
+            if torch.is_tensor(v):
+                st[k].copy_(v, non_blocking=True)
+        st["z_g"].copy_(z_g)
+        st["z_d"].copy_(z_d)
+        if host_batch["bbox_text"] != st["bbox_text"]:
+            st["bbox_text"] = host_batch["bbox_text"]
+            self._refresh_host_derived(st, host_batch["padding_mask"])
+        for name in ("G", "D"):
+            o = tr.opt[name]
+            tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
+        ent["graph"].replay()
+        tr.update_ema()                                          # EMA beta depends on the image counter: kept out of the graph
+        return ent["out"]
