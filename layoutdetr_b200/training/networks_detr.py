@@ -97,6 +97,9 @@ class _TextFrontEnd:
         self._val = None
 
     def __call__(self, bbox_text, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         flat = merge_lists(bbox_text)
         key = (tuple(flat), str(device))
         if key != self._key:
@@ -105,7 +108,7 @@ class _TextFrontEnd:
             ids, mask = enc.input_ids, enc.attention_mask
             text_len = torch.from_numpy(np.array([len(t) for t in flat], dtype=np.int64))
             old = self._val
-            if old is not None and old["ids"].shape == ids.shape and old["ids"].device == torch.device(device):
+            if old is not None and old["ids"].shape == ids.shape and old["ids"].device == device:
                 # refresh in place: device addresses stay stable (a captured CUDA graph keeps reading these buffers)
                 old["ids"].copy_(ids); old["mask"].copy_(mask); old["text_len"].copy_(text_len)
                 old["ids_cpu"], old["mask_cpu"] = ids, mask

@@ -103,6 +103,37 @@ class GraphedStep:
                 m.__dict__["_inv_n_valid"] = buf
             buf.fill_(1.0 / max(1, n))
 
+    def _snapshot(self):
+        tr = self.tr
+        snap = dict(cur_nimg=tr.cur_nimg, steps={n: f.step for n, f in tr.flat.items()})
+        for n, f in list(tr.flat.items()) + [("ema", tr.flat_ema)]:
+            snap[n] = (f.p.clone(), f.v.clone() if f.v is not None else None, f.m.clone() if f.m is not None else None)
+        return snap
+
+    def _restore(self, snap, st):
+        """Undo the warm-up / capture side effects and bring every derived bf16 shadow back in line with the weights."""
+        from .. import engine as E
+        from .. import kernels as K
+        tr = self.tr
+        tr.cur_nimg = snap["cur_nimg"]
+        for n, f in list(tr.flat.items()) + [("ema", tr.flat_ema)]:
+            p, v, m = snap[n]
+            f.p.copy_(p)
+            if v is not None:
+                f.v.copy_(v)
+            if m is not None:
+                f.m.copy_(m)
+            f.p16.copy_(K.to_bf16(f.p))
+            if n != "ema":
+                f.step = snap["steps"][n]
+            E.bump_generation(f.params)
+        with torch.no_grad():                                    # cache misses -> shadows recomputed in place (stable pointers)
+            tr.G(st["z_g"], st["bbox_class"], st["bbox_real"], st["bbox_text"], st["bbox_patch"], st["padding_mask"],
+                 st["background"], st["c"], reconst=True)
+            tr.D(st["bbox_real"], st["bbox_class"], st["bbox_text"], st["bbox_patch"], st["padding_mask"], st["background"],
+                 st["c"], reconst=True)
+        torch.cuda.synchronize()
+
     def run_static(self):
         """Replay the (single) captured graph on whatever the static input buffers currently hold (inputs resident in HBM)."""
         tr = self.tr
@@ -124,15 +155,14 @@ class GraphedStep:
             st = {k: (v.to(tr.device) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
             st["z_g"], st["z_d"] = z_g.clone(), z_d.clone()
             self._refresh_host_derived(st, host_batch["padding_mask"])
+            # Warm-up + capture must not train: snapshot weights / Adam state / counters and restore them afterwards.
+            snap = self._snapshot()
             # warm up on a side stream (allocator pools, lazy inits, shadow caches reach their steady state), then capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
                     tr.iteration(st, st["z_g"], st["z_d"])
-            for name in ("G", "D"):                              # the captured pass itself also counts as one optimizer step
-                o = tr.opt[name]
-                tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -143,7 +173,11 @@ class GraphedStep:
                 out = {ph: {k: v for k, v in terms.items()} for ph, terms in out.items()}
             ent = dict(graph=g, static=st, out=out, launches=_lib.launch_count() - n0)
             self.graphs[key] = ent
-            g.replay()                                           # capture does not execute: run the step once
+            self._restore(snap, st)
+            for name in ("G", "D"):
+                o = tr.opt[name]
+                tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
+            g.replay()                                           # the first real step on this batch
             tr.update_ema()
             return ent["out"]
         st = ent["static"]

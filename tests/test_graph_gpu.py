@@ -25,23 +25,33 @@ def test_graph_replay_matches_eager():
     from layoutdetr_b200.training.trainer import Trainer, GraphedStep
     hb = [make_inputs(2, n_valid=8, seed=s) for s in (1, 2, 3)]
     zs = [torch.randn((2, 9, 4), device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)) for i in range(6)]
-    results = []
+    results, losses = [], []
     for mode in ("eager", "graph"):
         engine.clear_cache()
         G, D = _small_models()
-        tr = Trainer(G, D, torch.device("cuda"), batch_size=2, lr=1e-3)
+        tr = Trainer(G, D, torch.device("cuda"), batch_size=2, lr=1e-5)
+        init = (tr.flat["G"].p.clone(), tr.flat["D"].p.clone(), tr.flat_ema.p.clone())
         gs = GraphedStep(tr) if mode == "graph" else None
+        ls = []
         for it in range(3):
             b = hb[it]
             if gs is not None:
-                gs.run(b, zs[2 * it], zs[2 * it + 1])
+                out = gs.run(b, zs[2 * it], zs[2 * it + 1])
             else:
                 dev_b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()}
-                tr.iteration(dev_b, zs[2 * it], zs[2 * it + 1])
+                out = tr.iteration(dev_b, zs[2 * it], zs[2 * it + 1])
+            ls.append(torch.stack([v.float().mean() for ph in ("Gmain", "Dmain") for v in out[ph].values()]).cpu())
         torch.cuda.synchronize()
-        results.append((tr.flat["G"].p.clone(), tr.flat["D"].p.clone(), tr.flat_ema.p.clone()))
-    for a, b, name in zip(results[0], results[1], ("G", "D", "G_ema")):
-        diff = float((a - b).abs().max())
-        scale = float(a.abs().max())
-        print(name, "max abs diff eager vs graph", diff, "scale", scale)
-        assert diff < 2e-3 * 1e-3 * 50 + 1e-6, (name, diff)     # a few Adam steps of lr 1e-3; atomics reorder fp32 sums
+        losses.append(torch.stack(ls))
+        results.append(tuple(f - i for f, i in zip((tr.flat["G"].p, tr.flat["D"].p, tr.flat_ema.p), init)))
+    print("loss terms eager vs graph, max rel diff per iteration:",
+          [float(((losses[0][i] - losses[1][i]).abs() / (losses[0][i].abs() + 1e-3)).max()) for i in range(3)])
+    for i in range(3):
+        print("iter", i, "eager", [round(float(x), 4) for x in losses[0][i]])
+        print("iter", i, "graph", [round(float(x), 4) for x in losses[1][i]])
+    for i in range(3):
+        torch.testing.assert_close(losses[0][i], losses[1][i], atol=2e-2, rtol=5e-2)
+    for ue, ug, name in zip(results[0], results[1], ("G", "D", "G_ema")):
+        rel = float((ue - ug).norm() / (ue.norm() + 1e-20))
+        print(name, "relative L2 difference of the accumulated update, eager vs graph: %.4f" % rel)
+        assert rel < 0.15, (name, rel)          # Adam turns ~0 gradients (atomics-order noise) into +-lr steps; real bugs give O(1)
