@@ -192,7 +192,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = bool(args.graph) and (world == 1 or os.environ.get("LD_GRAPH_MULTI", "0") == "1")
+    use_graph = bool(args.graph)
     gs = GraphedStep(trainer) if use_graph else None
     if gs is not None:
         gs.run(host_batches[0], zs[0], zs[1])               # warm-up + capture of the whole iteration

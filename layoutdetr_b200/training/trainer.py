@@ -38,6 +38,19 @@ class Trainer:
             m.requires_grad_(False)
 
     def _phase(self, name, batch, gen_z):
+        self._phase_grads(name, batch, gen_z)
+        self._phase_reduce(name)
+        self._phase_step(name)
+
+    def _phase_reduce(self, name):
+        if self.num_gpus > 1:
+            torch.distributed.all_reduce(self.flat[name].g, group=self.pg)
+
+    def _phase_step(self, name):
+        o = self.opt[name]
+        self.flat[name].adam_step(o["lr"], o["beta1"], o["beta2"], o["eps"], grad_scale=1.0 / self.num_gpus)
+
+    def _phase_grads(self, name, batch, gen_z):
         mod = self.G if name == "G" else self.D
         flat = self.flat[name]
         flat.zero_grad()
@@ -48,12 +61,6 @@ class Trainer:
                                        padding_mask=batch["padding_mask"], background=batch["background"], real_c=batch["c"],
                                        gen_z=gen_z, gen_c=batch["c"], gain=1, cur_nimg=self.cur_nimg)
         mod.requires_grad_(False)
-        scale = 1.0
-        if self.num_gpus > 1:
-            torch.distributed.all_reduce(flat.g, group=self.pg)
-            scale = 1.0 / self.num_gpus
-        o = self.opt[name]
-        flat.adam_step(o["lr"], o["beta1"], o["beta2"], o["eps"], grad_scale=scale)
 
     def iteration(self, batch, z_g, z_d, update_ema=True):
         self._phase("G", batch, z_g)
@@ -84,8 +91,8 @@ class GraphedStep:
 
     def _key(self, host_batch):
         pm = host_batch["padding_mask"]
-        flat_len = tuple(len(t) > 0 for row in host_batch["bbox_text"] for t in row)
-        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), flat_len[:0])
+        G = self.tr.G
+        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup))
 
     def _refresh_host_derived(self, st, host_mask):
         """Tokenise (host) into the front-ends' persistent device buffers and refresh the LM-loss normalisers."""
@@ -134,15 +141,24 @@ class GraphedStep:
                  st["c"], reconst=True)
         torch.cuda.synchronize()
 
-    def run_static(self):
-        """Replay the (single) captured graph on whatever the static input buffers currently hold (inputs resident in HBM)."""
+    def _replay(self, ent):
         tr = self.tr
-        ent = next(iter(self.graphs.values()))
         for name in ("G", "D"):
             o = tr.opt[name]
             tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
-        ent["graph"].replay()
-        tr.update_ema()
+        gr = ent["graphs"]
+        if len(gr) == 1:
+            gr[0].replay()
+        else:
+            gr[0].replay(); tr._phase_reduce("G")
+            gr[1].replay(); tr._phase_reduce("D")
+            gr[2].replay()
+        tr.update_ema()                                          # EMA beta depends on the image counter: kept out of the graph
+
+    def run_static(self):
+        """Replay the captured iteration on whatever the static input buffers currently hold (inputs resident in HBM)."""
+        ent = next(iter(self.graphs.values()))
+        self._replay(ent)
         return ent["out"]
 
     def run(self, host_batch, z_g, z_d):
@@ -165,20 +181,29 @@ class GraphedStep:
                     tr.iteration(st, st["z_g"], st["z_d"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
             from .. import _lib
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g):
-                out = tr.iteration(st, st["z_g"], st["z_d"], update_ema=False)
-                out = {ph: {k: v for k, v in terms.items()} for ph, terms in out.items()}
-            ent = dict(graph=g, static=st, out=out, launches=_lib.launch_count() - n0)
+            if tr.num_gpus == 1:
+                segs = [lambda: tr.iteration(st, st["z_g"], st["z_d"], update_ema=False)]
+            else:
+                # NCCL collectives stay outside the graphs: [Gmain grads] -AR- [Adam(G) + Dmain grads] -AR- [Adam(D)]
+                segs = [lambda: tr._phase_grads("G", st, st["z_g"]),
+                        lambda: (tr._phase_step("G"), tr._phase_grads("D", st, st["z_d"])),
+                        lambda: tr._phase_step("D")]
+            graphs, pool = [], None
+            for i, seg in enumerate(segs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg()
+                pool = g.pool()
+                graphs.append(g)
+                if tr.num_gpus > 1 and i < len(segs) - 1:       # keep the eager state consistent between captures
+                    torch.cuda.synchronize()
+            out = {ph: {k: v for k, v in terms.items()} for ph, terms in tr.loss.last.items()}
+            ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0)
             self.graphs[key] = ent
             self._restore(snap, st)
-            for name in ("G", "D"):
-                o = tr.opt[name]
-                tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
-            g.replay()                                           # the first real step on this batch
-            tr.update_ema()
+            self._replay(ent)                                    # the first real step on this batch
             return ent["out"]
         st = ent["static"]
         for k, v in host_batch.items():
@@ -189,9 +214,5 @@ class GraphedStep:
         if host_batch["bbox_text"] != st["bbox_text"]:
             st["bbox_text"] = host_batch["bbox_text"]
             self._refresh_host_derived(st, host_batch["padding_mask"])
-        for name in ("G", "D"):
-            o = tr.opt[name]
-            tr.flat[name].set_hyper(o["lr"], o["beta1"], o["beta2"])
-        ent["graph"].replay()
-        tr.update_ema()                                          # EMA beta depends on the image counter: kept out of the graph
+        self._replay(ent)
         return ent["out"]
