@@ -135,6 +135,13 @@ def _host_mask(padding_mask):
 
 
 _valid_idx_cache = {}
+_ITERATION = [0]
+
+
+def new_iteration():
+    """Marks the start of a training iteration: per-iteration caches (frozen text-encoder features under `text_dedup`)
+    are only valid within one iteration."""
+    _ITERATION[0] += 1
 
 
 def valid_index(padding_mask):
@@ -161,7 +168,7 @@ def _encode_text(module, text, B, N):
         ids, mask = ids[:, :T].contiguous(), mask[:, :T].contiguous()
     frozen = not any(p.requires_grad for p in enc.parameters())
     if module.text_dedup and frozen:
-        key = (id(text["ids"]), ids.shape[1], tuple(p._version for p in enc.parameters()))
+        key = (_ITERATION[0], id(text["ids"]), ids.shape[1], tuple(p._version for p in enc.parameters()))
         if module._cls_cache is not None and module._cls_cache[0] == key:
             return module._cls_cache[1]
         with torch.no_grad():

@@ -51,6 +51,9 @@ class Trainer:
         self.flat[name].adam_step(o["lr"], o["beta1"], o["beta2"], o["eps"], grad_scale=1.0 / self.num_gpus)
 
     def _phase_grads(self, name, batch, gen_z):
+        if name == "G":
+            from . import networks_detr as nd
+            nd.new_iteration()
         mod = self.G if name == "G" else self.D
         flat = self.flat[name]
         flat.zero_grad()
