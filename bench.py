@@ -154,6 +154,8 @@ def run_ours(args):
     from layoutdetr_b200.synthetic import make_inputs
     from layoutdetr_b200.training import networks_detr as nd
     from layoutdetr_b200.training.trainer import Trainer, GraphedStep
+    from layoutdetr_b200.lanes import LANES
+    LANES.configure(level=args.lanes, text_ctas=args.text_ctas, lm_ctas=args.lm_ctas, high_priority=args.lane_priority)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -307,7 +309,9 @@ def run_ours(args):
                                 batch_per_gpu=B, global_batch=B * world, text_tokens=256, text_trim=bool(args.text_trim),
                                 text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
                                 dropout="off (deterministic eval-semantics kernels)", parallelism="dp%d" % world,
-                                launch="cuda graph replay of the captured iteration" if gs is not None else "eager (one launch per kernel)"),
+                                launch="cuda graph replay of the captured iteration" if gs is not None else "eager (one launch per kernel)",
+                                lanes=dict(level=LANES.level, text_ctas=LANES.text_ctas, lm_ctas=LANES.lm_ctas, priority=LANES.high_priority,
+                                           note="independent sub-graphs of the iteration on parallel streams (same kernels, same operands)")),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, variants=[variant] if variant else [])
         print(json.dumps(line), flush=True)
@@ -326,6 +330,10 @@ def main():
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
     ap.add_argument("--graph", type=int, default=1, help="1: capture the iteration into a CUDA graph (single-GPU default)")
     ap.add_argument("--variants", type=int, default=1, help="1: also time the exact work-saving variant (reported separately)")
+    ap.add_argument("--lanes", type=int, default=None, help="lane scheduler level 0..3 (layoutdetr_b200/lanes.py); default: LD_LANES or 3")
+    ap.add_argument("--text-ctas", type=int, default=None, help="persistent-GEMM grid cap of the text-encoder lane")
+    ap.add_argument("--lm-ctas", type=int, default=None, help="persistent-GEMM grid cap of the text-decoder branches")
+    ap.add_argument("--lane-priority", type=int, default=None, help="1: latency-bound lanes get a higher stream priority")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu", action="store_true", help="profile exactly one resident step between cudaProfilerStart/Stop and exit")
     ap.add_argument("--steps-ref", type=int, default=1)

@@ -33,6 +33,12 @@ int ld_version(void);
 /* number of kernels launched by this library since load / since the last reset (bench.py gpu_launches) */
 int64_t ld_launch_count(void);
 void ld_launch_count_reset(void);
+/* Lane scheduling: cap the grid of the persistent kernels (ld_gemm_bf16) launched on `stream` at `limit` CTAs
+ * (<= 0 clears the cap; default = one CTA per SM).  The host runs independent parts of the iteration on parallel
+ * streams — the frozen text encoder (training/networks_detr.py:146) next to the latency-bound DETR / ResNet chains —
+ * and a capped tensor-bound lane leaves SMs for the others.  The reference has no counterpart (single stream). */
+int ld_set_stream_cta_limit(void* stream, int limit);
+int ld_get_stream_cta_limit(void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched bf16 GEMM on tcgen05 tensor cores (TMA-staged SWIZZLE_128B tiles, TMEM accumulators)

@@ -28,6 +28,7 @@ static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // number of SMs of the current device (cached)
 int sm_count();
+int cta_limit_for(void* stream);   // min(SM count, ld_set_stream_cta_limit of this stream)
 
 // ---------------------------------------------------------------------------------------------
 // small device utilities

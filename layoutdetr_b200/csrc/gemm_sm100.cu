@@ -624,6 +624,7 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     p.softmax = d->softmax ? 1 : 0; p.causal = d->causal ? 1 : 0; p.mask_value = d->mask_value; p.key_mask = d->key_mask;
 
     const int sms = sm_count();
+    const int cta_limit = cta_limit_for(stream);       // persistent grid cap of this stream's lane (default: every SM)
     // CTA pairs (cta_group::2) for problems with enough 256 x 256 tiles to fill the chip: opt-in with LD_GEMM_2SM=1
     // (measured neutral on B200 for the BERT shapes: the 1-CTA mainloop is clock/power- rather than L2-limited)
     static const int env_2sm = [] { const char* e = getenv("LD_GEMM_2SM"); return e ? atoi(e) : 0; }();
@@ -679,10 +680,11 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
         attr_set = true;
     }
     if (two_sm) {
-        const int pairs = (int)(total < sms / 2 ? total : sms / 2);
+        const int cap2 = cta_limit / 2 > 0 ? cta_limit / 2 : 1;
+        const int pairs = (int)(total < cap2 ? total : cap2);
         gemm_bf16_2sm_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
     } else {
-        const int grid = (int)(total < sms ? total : sms);
+        const int grid = (int)(total < cta_limit ? total : cta_limit);
         gemm_bf16_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
     }
     count_launch();

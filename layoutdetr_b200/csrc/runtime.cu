@@ -42,6 +42,20 @@ int sm_count() {
     return cached[dev];
 }
 
+// Per-stream cap on the number of CTAs a persistent kernel may occupy (ld_set_stream_cta_limit): lets the host run
+// a tensor-bound lane (frozen text encoder) next to latency-bound lanes without one kernel holding every SM.
+static std::mutex g_lim_mu;
+static struct { void* stream; int limit; } g_lims[32];
+static int g_nlims = 0;
+
+int cta_limit_for(void* stream) {
+    const int sms = sm_count();
+    std::lock_guard<std::mutex> lk(g_lim_mu);
+    for (int i = 0; i < g_nlims; ++i)
+        if (g_lims[i].stream == stream) return g_lims[i].limit < sms ? g_lims[i].limit : sms;
+    return sms;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -90,4 +104,23 @@ const char* ld_last_error(void) { return ld::g_err; }
 int ld_version(void) { return 100; }
 int64_t ld_launch_count(void) { return ld::g_launches.load(); }
 void ld_launch_count_reset(void) { ld::g_launches.store(0); }
+
+int ld_set_stream_cta_limit(void* stream, int limit) {
+    std::lock_guard<std::mutex> lk(ld::g_lim_mu);
+    int i = 0;
+    for (; i < ld::g_nlims; ++i) if (ld::g_lims[i].stream == stream) break;
+    if (limit <= 0) {                                   // clear
+        if (i < ld::g_nlims) ld::g_lims[i] = ld::g_lims[--ld::g_nlims];
+        return 0;
+    }
+    if (i == ld::g_nlims) {
+        if (ld::g_nlims == 32) { ld::set_last_error("ld_set_stream_cta_limit: more than 32 limited streams"); return LD_ERR_INVALID_ARG; }
+        ++ld::g_nlims;
+    }
+    ld::g_lims[i].stream = stream;
+    ld::g_lims[i].limit = limit;
+    return 0;
+}
+
+int ld_get_stream_cta_limit(void* stream) { return ld::cta_limit_for(stream); }
 }

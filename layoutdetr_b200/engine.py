@@ -5,11 +5,13 @@ optimizer updates them, `state_dict` keys match the reference).  Tensor cores re
 are refreshed lazily whenever a parameter's version counter changes (optimizer step, load_state_dict,
 EMA copy).
 """
+import weakref
+
 import torch
 
 from . import kernels as K
 
-_shadow = {}          # (id(param), tag) -> (version, data_ptr, generation, tensor)
+_shadow = {}          # (id(param), tag) -> (version, data_ptr, generation, tensor, params, make_fn)
 _managed = {}         # id(param) -> bf16 [N, K] view kept fresh by the fused optimizer kernel (flat storage)
 _generation = {}      # id(param) -> int, bumped when a kernel rewrites the parameter through a raw pointer
 _SM_COUNT = None
@@ -52,7 +54,7 @@ def _lookup(key, params):
     return None
 
 
-def _store(key, params, value):
+def _store(key, params, value, fn=None):
     # Refresh IN PLACE when a previous shadow of the same shape exists: the device address of a derived shadow must stay
     # stable so that a captured CUDA graph (which bakes pointers) keeps reading the buffer a later refresh writes.
     old = _shadow.get(key)
@@ -60,9 +62,35 @@ def _store(key, params, value):
             and old[3].device == value.device:
         old[3].copy_(value)
         value = old[3]
+    if fn is None and old is not None:
+        fn = old[5]
     _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
-                    tuple(_generation.get(id(p), 0) for p in params), value)
+                    tuple(_generation.get(id(p), 0) for p in params), value, tuple(weakref.ref(p) for p in params), fn)
     return value
+
+
+def refresh_stale(only_ids=None):
+    """Recompute (in place) every cached shadow whose source parameters changed since it was made, on the CURRENT stream.
+    The lane scheduler (lanes.py) calls this before it forks: a shadow refreshed lazily inside one lane would race with
+    readers in another lane.  Plain weight shadows first — concatenations are built from them.  `only_ids`: restrict to
+    shadows derived from parameters / buffers with these `id()`s (the modules the caller is about to run)."""
+    stale = []
+    for key, ent in list(_shadow.items()):
+        params = tuple(r() for r in ent[4])
+        if any(p is None for p in params):          # the module is gone
+            del _shadow[key]
+            continue
+        if ent[5] is None or (only_ids is not None and not all(id(p) in only_ids for p in params)):
+            continue
+        if ent[0] != tuple(p._version for p in params) or ent[1] != tuple(p.data_ptr() for p in params) or \
+                ent[2] != tuple(_generation.get(id(p), 0) for p in params):
+            stale.append((0 if key[1] == "w" else 1, key, params, ent[5]))
+    stale.sort(key=lambda t: t[0])
+    for _, key, params, fn in stale:
+        with torch.no_grad():
+            v = fn()
+        _store(key, params, v, fn)
+    return len(stale)
 
 
 def pad8(n):
@@ -77,11 +105,13 @@ def w_bf16(param):
     key = (id(param), "w")
     v = _lookup(key, (param,))
     if v is None:
-        with torch.no_grad():
+        def make():
             w = param.detach()
             w2 = w.reshape(w.shape[0], -1)
-            v = K.cast_pad(w2, torch.bfloat16, pad8(w2.shape[1]))
-        _store(key, (param,), v)
+            return K.cast_pad(w2, torch.bfloat16, pad8(w2.shape[1]))
+        with torch.no_grad():
+            v = make()
+        v = _store(key, (param,), v, make)
     return v
 
 
@@ -90,9 +120,10 @@ def w_cat_bf16(params):
     key = (tuple(id(p) for p in params), "cat")
     v = _lookup(key, params)
     if v is None:
+        make = lambda: torch.cat([w_bf16(p) for p in params], dim=0)
         with torch.no_grad():
-            v = torch.cat([w_bf16(p) for p in params], dim=0)
-        _store(key, params, v)
+            v = make()
+        v = _store(key, params, v, make)
     return v
 
 
@@ -100,9 +131,10 @@ def b_cat_f32(params):
     key = (tuple(id(p) for p in params), "bcat")
     v = _lookup(key, params)
     if v is None:
+        make = lambda: torch.cat([p.detach().float() for p in params], dim=0).contiguous()
         with torch.no_grad():
-            v = torch.cat([p.detach().float() for p in params], dim=0).contiguous()
-        _store(key, params, v)
+            v = make()
+        v = _store(key, params, v, make)
     return v
 
 
@@ -114,7 +146,7 @@ def derived(param_tuple, tag, fn):
     if v is None:
         with torch.no_grad():
             v = fn()
-        _store(key, param_tuple, v)
+        v = _store(key, param_tuple, v, fn)
     return v
 
 

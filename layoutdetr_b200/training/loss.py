@@ -10,7 +10,15 @@ import torch.nn.functional as F
 from ..metrics.metric_layoutnet import generalized_iou_loss, compute_overlap, compute_alignment
 from ..torch_utils import training_stats
 from .. import functional as Fn
+from ..lanes import LANES
 from .networks_detr import valid_index
+
+
+def _after_backward():
+    """Backward kernels run on the lanes (streams) of their forward and add into parameter gradients as a side effect
+    autograd does not see: the issuing stream waits for them here (lanes.py)."""
+    if LANES.active(2):
+        LANES.join_children()
 
 
 class Loss:
@@ -43,8 +51,13 @@ class StyleGAN2Loss(Loss):
     def run_D(self, bbox, bbox_class, bbox_text, bbox_patch, padding_mask, background, c, reconst=False, blur_sigma=0, update_emas=False):
         return self.D(bbox, bbox_class, bbox_text, bbox_patch, padding_mask, background, c, reconst)
 
-    def accumulate_gradients(self, phase, bbox_real, bbox_class, bbox_text, bbox_patch, padding_mask, background, real_c, gen_z, gen_c, gain, cur_nimg):
-        assert phase in ['Gmain', 'Greg', 'Gboth', 'Dmain', 'Dreg', 'Dboth']
+    def accumulate_gradients(self, phase, bbox_real, bbox_class, bbox_text, bbox_patch, padding_mask, background, real_c, gen_z, gen_c, gain, cur_nimg,
+                             before_backward=None):
+        """Phases as in the reference, plus 'Dgen' / 'Dreal': the two halves of 'Dmain' (fake-sample pass :146-157 and
+        real-sample pass :161-218), which the lane scheduler issues on different streams.  `before_backward` is called
+        right before each `.backward()` (stream ordering hook)."""
+        assert phase in ['Gmain', 'Greg', 'Gboth', 'Dmain', 'Dreg', 'Dboth', 'Dgen', 'Dreal']
+        pre_bwd = before_backward if before_backward is not None else (lambda: None)
         if self.pl_weight == 0:
             phase = {'Greg': 'none', 'Gboth': 'Gmain'}.get(phase, phase)
         if self.r1_gamma == 0:
@@ -77,9 +90,12 @@ class StyleGAN2Loss(Loss):
             for k, v in terms.items():
                 report('Loss/G/' + k, v)
             self.last['Gmain'] = {k: v.detach() for k, v in terms.items()}
-            sum(terms.values()).mean().mul(gain).backward()
+            loss = sum(terms.values()).mean().mul(gain)
+            pre_bwd()
+            loss.backward()
+            _after_backward()
 
-        if phase == 'Dmain':
+        if phase in ('Dmain', 'Dgen'):
             with torch.no_grad():
                 bbox_fake = self.run_G(gen_z, bbox_class, bbox_real, bbox_text, bbox_patch, padding_mask, background, gen_c, update_emas=True)
             gen_logits, gen_logits_uncond = self.run_D(bbox_fake, bbox_class, bbox_text, bbox_patch, padding_mask, background, gen_c, update_emas=True)
@@ -88,8 +104,13 @@ class StyleGAN2Loss(Loss):
             loss_Dgen_uncond = F.softplus(gen_logits_uncond)
             report('Loss/D/loss_Dgen', loss_Dgen)
             report('Loss/D/loss_Dgen_uncond', loss_Dgen_uncond)
-            (loss_Dgen + loss_Dgen_uncond).mean().mul(gain).backward()
+            self.last.setdefault('Dmain', {}).update(loss_Dgen=loss_Dgen.detach(), loss_Dgen_uncond=loss_Dgen_uncond.detach())
+            loss = (loss_Dgen + loss_Dgen_uncond).mean().mul(gain)
+            pre_bwd()
+            loss.backward()
+            _after_backward()
 
+        if phase in ('Dmain', 'Dreal'):
             bbox_real_tmp = bbox_real.detach()
             (real_logits, real_logits_uncond, bbox_rec, cls_logits, loss_lm, loss_text_len, bg_rec, bbox_rec_uncond,
              cls_logits_uncond) = self.run_D(bbox_real_tmp, bbox_class, bbox_text, bbox_patch, padding_mask, background, real_c, reconst=True)
@@ -108,5 +129,8 @@ class StyleGAN2Loss(Loss):
             )
             for k, v in terms.items():
                 report('Loss/D/' + k, v)
-            self.last['Dmain'] = dict({k: v.detach() for k, v in terms.items()}, loss_Dgen=loss_Dgen.detach(), loss_Dgen_uncond=loss_Dgen_uncond.detach())
-            sum(terms.values()).mean().mul(gain).backward()
+            self.last.setdefault('Dmain', {}).update({k: v.detach() for k, v in terms.items()})
+            loss = sum(terms.values()).mean().mul(gain)
+            pre_bwd()
+            loss.backward()
+            _after_backward()

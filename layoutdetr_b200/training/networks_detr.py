@@ -8,6 +8,7 @@ StyleGAN2 background decoder) runs in hand-written CUDA through layoutdetr_b200.
 ops appear only as glue on tiny tensors (concatenation / indexing of `[B*9, d]` rows, scalar losses).
 There is no CPU path: inputs must live on a CUDA device.
 """
+import collections
 import os
 
 import numpy as np
@@ -17,6 +18,7 @@ import torch.nn.functional as F
 
 from .. import functional as Fn
 from .. import kernels as K
+from ..lanes import LANES
 from .detr_backbone import build_backbone as _build_backbone
 from .detr_transformer import Transformer, TransformerWithToken, TransformerEncoderStack
 from .med import BertConfig, BertModel, BertLMHeadModel
@@ -158,8 +160,8 @@ def valid_index(padding_mask):
     return v
 
 
-def _encode_text(module, text, B, N):
-    """CLS feature of the frozen/unfrozen text encoder for every slot -> bf16 [B*N, bert_f_dim]."""
+def _encode_text_now(module, text):
+    """Runs the text encoder on the current stream -> bf16 [B*N, bert_f_dim] CLS features."""
     enc = module.text_encoder
     ids, mask = text["ids"], text["mask"]
     if module.text_trim:
@@ -176,6 +178,41 @@ def _encode_text(module, text, B, N):
         module._cls_cache = (key, feat)
         return feat
     return enc.cls_features(ids, mask).contiguous()
+
+
+def prefetch_text(modules, bbox_text, device):
+    """Lane scheduling (lanes.py, level 1): issue the frozen text-encoder call of every module in `modules` (one entry
+    per forward pass that will follow, in the order the passes are issued on the host) on the T lane.  Each module's
+    `_encode_text` then pops its result and makes the consuming stream wait for that call only.  The encoder's only
+    inputs are the token ids (reference training/networks_detr.py:145-147), so hoisting the calls changes nothing."""
+    texts = {id(m): m._front()(bbox_text, device) for m in modules}          # token ids reach the device on this stream
+    sT = LANES.fork("T", cta_limit=LANES.text_ctas, bulk=True, detached=True)
+    with torch.cuda.stream(sT), torch.no_grad():
+        for m in modules:
+            if any(p.requires_grad for p in m.text_encoder.parameters()):
+                raise RuntimeError("prefetch_text needs a frozen text encoder (training/training_loop.py:283)")
+            feat = _encode_text_now(m, texts[id(m)])
+            ev = torch.cuda.Event()
+            ev.record(sT)
+            m.__dict__.setdefault("_te_queue", collections.deque()).append([feat, ev])
+    return sT
+
+
+def pending_text(modules):
+    return sum(len(m.__dict__.get("_te_queue", ())) for m in modules)
+
+
+def _encode_text(module, text, B, N):
+    """CLS feature of the frozen/unfrozen text encoder for every slot -> bf16 [B*N, bert_f_dim]."""
+    q = module.__dict__.get("_te_queue")
+    if q:
+        feat, ev = q.popleft()
+        cur = torch.cuda.current_stream()
+        if ev is not None:
+            cur.wait_event(ev)
+        feat.record_stream(cur)
+        return feat
+    return _encode_text_now(module, text)
 
 
 def lm_target_count(text, valid_idx_cpu, pad_id, trim=False):
@@ -278,6 +315,17 @@ class Generator(nn.Module):
         B, N = bbox_patch.shape[0], bbox_patch.shape[1]
         H = self.hidden_dim
 
+        # lane scheduling (lanes.py, level 2): the text-decoder LM loss depends on the token ids only
+        branches = reconst and LANES.active(2)
+        text = self._front()(bbox_text, dev)
+        s_td = loss_lm = None
+        if reconst:
+            valid, valid_cpu = valid_index(padding_mask)
+        if branches:
+            s_td = LANES.fork("td", cta_limit=LANES.lm_ctas, bulk=True)
+            with torch.cuda.stream(s_td):
+                loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+
         feat, pos, h, w = self.backbone(background.float())
         S = h * w
         src = Fn.conv2d(feat, self.input_proj.weight, None, self.input_proj.bias, None, B, h, w, 1, 0, K.ACT_NONE)
@@ -285,7 +333,6 @@ class Generator(nn.Module):
         z0 = normalize_2nd_moment(z.reshape(B, -1).float())
         zf = Fn.linear(Fn.to_bf16_padded(z0), self.fc_z.weight, self.fc_z.bias)                     # [B, 768]
         l = F.embedding(bbox_class, self.emb_label.weight)                                          # [B, N, 768]
-        text = self._front()(bbox_text, dev)
         text_feat = _encode_text(self, text, B, N)                                                  # [B*N, 768] bf16
         text_len = text["text_len"].view(B, N)
         text_len_feat = F.embedding(text_len, self.enc_text_len.weight)
@@ -298,15 +345,17 @@ class Generator(nn.Module):
         if not reconst:
             return bbox_fake
 
-        valid, valid_cpu = valid_index(padding_mask)
         xv = hs.index_select(0, valid)                                                              # [M, 256]
         z_rec = Fn.linear_f32(xv, self.fc_z_rec.weight, self.fc_z_rec.bias)
         z_tgt = z0.unsqueeze(1).expand(-1, N, -1).reshape(B * N, -1).index_select(0, valid)
         loss_z = F.mse_loss(z_rec, z_tgt)
         logit_cls = Fn.linear_f32(xv, self.fc_out_cls.weight, self.fc_out_cls.bias)
-        loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+        if s_td is None:
+            loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
         text_len_rec = Fn.linear_f32(xv, self.fc_text_len_rec.weight, self.fc_text_len_rec.bias)
         loss_text_len = Fn.cross_entropy(text_len_rec, text_len.reshape(-1).index_select(0, valid))
+        if s_td is not None:
+            LANES.join(s_td, loss_lm)
         return bbox_fake, loss_z, logit_cls, loss_lm, loss_text_len
 
 
@@ -404,14 +453,50 @@ class Discriminator(nn.Module):
         B, N = bbox_patch.shape[0], bbox_patch.shape[1]
         H = self.hidden_dim
 
+        # lane scheduling (lanes.py, level 2): branches that do not depend on the conditional DETR chain run beside it —
+        # the LM text decoder (token ids only), the unconditional branch (boxes / classes only), the background decoder
+        # (token output only).  Single-stream when lanes are off: same calls, same order as the reference (:279-361).
+        branches = LANES.active(2)
+        text = self._front()(bbox_text, dev)
+        s_td = s_un = s_bg = loss_lm = bg_rec = None
+        valid = valid_cpu = None
+        if reconst:
+            valid, valid_cpu = valid_index(padding_mask)
+        if branches and reconst:
+            s_td = LANES.fork("td", cta_limit=LANES.lm_ctas, bulk=True)
+            with torch.cuda.stream(s_td):
+                loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+
+        bbox2d = Fn.to_bf16_padded(bbox.reshape(B * N, 4).float())
+
+        def uncond():
+            b_u = Fn.linear(bbox2d, self.fc_bbox_uncond.weight, self.fc_bbox_uncond.bias)
+            l_u = F.embedding(bbox_class, self.emb_label_uncond.weight)
+            x_u = torch.cat([b_u.view(B, N, -1), l_u.to(torch.bfloat16)], dim=-1).reshape(B * N, -1)
+            x_u = self.enc_fc_in_uncond(x_u, final_act=K.ACT_RELU)
+            x_u = self.enc_transformer_uncond(x_u, B, N, padding_mask)                              # [B*(N+1), 256]
+            x0_u = x_u.view(B, N + 1, H)[:, 0, :]
+            logit_u = Fn.linear_f32(x0_u, self.fc_out_disc_uncond.weight, self.fc_out_disc_uncond.bias).squeeze(-1)
+            if not reconst:
+                return logit_u, None, None
+            xv_u = self._decode_branch(x0_u, self.pos_token_uncond, self.dec_fc_in_uncond, self.dec_transformer_uncond,
+                                       B, N, padding_mask, valid)
+            bbox_u = Fn.linear_f32(xv_u, self.bbox_embed_uncond.weight, self.bbox_embed_uncond.bias).sigmoid()
+            cls_u = Fn.linear_f32(xv_u, self.fc_out_cls_uncond.weight, self.fc_out_cls_uncond.bias)
+            return logit_u, bbox_u, cls_u
+
+        un_out = None
+        if branches:
+            s_un = LANES.fork("un", bbox2d, bbox_class, padding_mask)
+            with torch.cuda.stream(s_un):
+                un_out = uncond()
+
         feat, pos, h, w = self.backbone(background.float())
         S = h * w
         src = Fn.conv2d(feat, self.input_proj.weight, None, self.input_proj.bias, None, B, h, w, 1, 0, K.ACT_NONE)
 
-        bbox2d = Fn.to_bf16_padded(bbox.reshape(B * N, 4).float())
         b = Fn.linear(bbox2d, self.fc_bbox.weight, self.fc_bbox.bias)                               # [B*N, 768]
         l = F.embedding(bbox_class, self.emb_label.weight)
-        text = self._front()(bbox_text, dev)
         text_feat = _encode_text(self, text, B, N)
         text_len = text["text_len"].view(B, N)
         text_len_feat = F.embedding(text_len, self.enc_text_len.weight)
@@ -421,30 +506,32 @@ class Discriminator(nn.Module):
 
         hs, _, L = self.enc_transformer(src, pos, x, padding_mask, B, S, N)                         # [B*(N+1), 256]
         x0 = hs.view(B, L, H)[:, 0, :]                                                              # token output
+        if branches and reconst:
+            s_bg = LANES.fork("bg", x0)
+            with torch.cuda.stream(s_bg):
+                bg_rec = self.bg_decoder(x0)
         logit_disc = Fn.linear_f32(x0, self.fc_out_disc.weight, self.fc_out_disc.bias).squeeze(-1)
 
-        b_u = Fn.linear(bbox2d, self.fc_bbox_uncond.weight, self.fc_bbox_uncond.bias)
-        l_u = F.embedding(bbox_class, self.emb_label_uncond.weight)
-        x_u = torch.cat([b_u.view(B, N, -1), l_u.to(torch.bfloat16)], dim=-1).reshape(B * N, -1)
-        x_u = self.enc_fc_in_uncond(x_u, final_act=K.ACT_RELU)
-        x_u = self.enc_transformer_uncond(x_u, B, N, padding_mask)                                  # [B*(N+1), 256]
-        x0_u = x_u.view(B, N + 1, H)[:, 0, :]
-        logit_disc_uncond = Fn.linear_f32(x0_u, self.fc_out_disc_uncond.weight, self.fc_out_disc_uncond.bias).squeeze(-1)
+        if not branches:
+            un_out = uncond()
         if not reconst:
-            return logit_disc, logit_disc_uncond
+            if s_un is not None:
+                LANES.join(s_un, un_out[0])
+            return logit_disc, un_out[0]
 
-        valid, valid_cpu = valid_index(padding_mask)
         xv = self._decode_branch(x0, self.pos_token, self.dec_fc_in, self.dec_transformer, B, N, padding_mask, valid)
         bbox_pred = Fn.linear_f32(xv, self.bbox_embed.weight, self.bbox_embed.bias).sigmoid()
         logit_cls = Fn.linear_f32(xv, self.fc_out_cls.weight, self.fc_out_cls.bias)
-        loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
+        if s_td is None:
+            loss_lm = _decode_text_loss(self, text, valid, valid_cpu, self.tokenizer.bos_token_id, self.tokenizer.pad_token_id)
         text_len_rec = Fn.linear_f32(xv, self.fc_text_len_rec.weight, self.fc_text_len_rec.bias)
         loss_text_len = Fn.cross_entropy(text_len_rec, text_len.reshape(-1).index_select(0, valid))
-        bg_rec = self.bg_decoder(x0)
-
-        xv_u = self._decode_branch(x0_u, self.pos_token_uncond, self.dec_fc_in_uncond, self.dec_transformer_uncond,
-                                   B, N, padding_mask, valid)
-        bbox_pred_uncond = Fn.linear_f32(xv_u, self.bbox_embed_uncond.weight, self.bbox_embed_uncond.bias).sigmoid()
-        logit_cls_uncond = Fn.linear_f32(xv_u, self.fc_out_cls_uncond.weight, self.fc_out_cls_uncond.bias)
+        if s_bg is None:
+            bg_rec = self.bg_decoder(x0)
+        logit_disc_uncond, bbox_pred_uncond, logit_cls_uncond = un_out
+        if branches:
+            LANES.join(s_un, logit_disc_uncond, bbox_pred_uncond, logit_cls_uncond)
+            LANES.join(s_td, loss_lm)
+            LANES.join(s_bg, bg_rec)
         return (logit_disc, logit_disc_uncond, bbox_pred, logit_cls, loss_lm, loss_text_len, bg_rec,
                 bbox_pred_uncond, logit_cls_uncond)

@@ -6,13 +6,19 @@ Differences from the reference are mechanical, not numerical:
     on the gradient buffer (no torch.cat / split) and nan_to_num + Adam + bf16 refresh is one kernel;
   * the EMA skips parameters that cannot change (the frozen text encoder) — lerp(p, p, beta) == p;
   * Greg / Dreg are no-ops at the reference defaults (pl_weight = r1_gamma = 0: zero_grad + an optimizer step
-    over parameters without gradients), so they launch nothing.
+    over parameters without gradients), so they launch nothing;
+  * independent parts of the iteration run on parallel CUDA streams (lanes.py): the frozen text-encoder calls, the
+    branches of a forward pass that do not feed each other, and the real-sample discriminator pass (which does not
+    depend on G) next to Gmain.  Same kernels, same operands; `LD_LANES=0` gives the single-stream schedule.
 """
 import copy
 
 import torch
 
+from .. import engine as E
 from ..flat import FlatParams
+from ..lanes import LANES
+from . import networks_detr as nd
 from .loss import StyleGAN2Loss
 
 
@@ -36,6 +42,16 @@ class Trainer:
         self.cur_nimg = 0
         for m in (G, D, self.G_ema):
             m.requires_grad_(False)
+        # lane scheduler state: the first iteration of a Trainer runs single-stream (fills every lazily built host cache)
+        self._warmed = False
+        self._iter_open = False
+        self._lanes_on = False
+        self._real_lane = None
+        self._text_lane = None
+        self._real_issued = False
+        self._suspending = False
+        self._param_ids = None
+        self.segmented = False               # True: _phase_grads("G") ends a CUDA-graph segment (multi-GPU, NCCL between graphs)
 
     def _phase(self, name, batch, gen_z):
         self._phase_grads(name, batch, gen_z)
@@ -50,22 +66,110 @@ class Trainer:
         o = self.opt[name]
         self.flat[name].adam_step(o["lr"], o["beta1"], o["beta2"], o["eps"], grad_scale=1.0 / self.num_gpus)
 
-    def _phase_grads(self, name, batch, gen_z):
-        if name == "G":
-            from . import networks_detr as nd
-            nd.new_iteration()
-        mod = self.G if name == "G" else self.D
-        flat = self.flat[name]
-        flat.zero_grad()
-        mod.requires_grad_(True)
-        mod.text_encoder.requires_grad_(False)
-        self.loss.accumulate_gradients(phase=name + "main", bbox_real=batch["bbox_real"], bbox_class=batch["bbox_class"],
+    def _accumulate(self, phase, batch, gen_z, before_backward=None):
+        self.loss.accumulate_gradients(phase=phase, bbox_real=batch["bbox_real"], bbox_class=batch["bbox_class"],
                                        bbox_text=batch["bbox_text"], bbox_patch=batch["bbox_patch"],
                                        padding_mask=batch["padding_mask"], background=batch["background"], real_c=batch["c"],
-                                       gen_z=gen_z, gen_c=batch["c"], gain=1, cur_nimg=self.cur_nimg)
+                                       gen_z=gen_z, gen_c=batch["c"], gain=1, cur_nimg=self.cur_nimg,
+                                       before_backward=before_backward)
+
+    def _phase_grads(self, name, batch, gen_z):
+        """Forward + backward of phase Gmain / Dmain into the flat gradient buffer (no reduce, no step)."""
+        if name == "G" and not self._iter_open:
+            self.begin_iteration(batch)
+        mod = self.G if name == "G" else self.D
+        split = name == "D" and self._real_issued                   # the real-sample half already ran on the R lane
+        if not split:
+            self.flat[name].zero_grad()
+        mod.requires_grad_(True)
+        mod.text_encoder.requires_grad_(False)
+        if split:
+            # both halves of Dmain add into the same gradient buffers: the fake-sample backward starts after the R lane
+            self._accumulate("Dgen", batch, gen_z, before_backward=self._join_real_lane)
+        else:
+            self._accumulate(name + "main", batch, gen_z)
+        if self._lanes_on:
+            LANES.join_children()            # backward kernels ran on the lanes of their forward
         mod.requires_grad_(False)
+        if name == "D":
+            self.end_iteration()
+        elif self.segmented:
+            self.join_lanes()                # a CUDA-graph segment ends here: every lane has to be back
+
+    # ---------------------------------------------------------------------------------------------- lane scheduling
+    def begin_iteration(self, batch):
+        """Start of an iteration: per-iteration caches, and with lanes on: refresh everything derived from the weights on
+        this stream, issue the five text-encoder calls on the T lane and the real-sample discriminator pass on the R lane."""
+        nd.new_iteration()
+        self._iter_open = True
+        self._real_issued = False
+        self._real_lane = self._text_lane = None
+        self._lanes_on = LANES.active(1) and self._warmed
+        if not self._warmed:                 # first iteration of this Trainer: single stream, fills every lazy host cache
+            LANES._suspended += 1
+            self._suspending = True
+        if not self._lanes_on:
+            return
+        G, D = self.G, self.D
+        if self._param_ids is None:
+            self._param_ids = set(id(t) for m in (G, D) for t in list(m.parameters()) + list(m.buffers()))
+        E.refresh_stale(self._param_ids)
+        for m in (G, D):
+            m._front()(batch["bbox_text"], self.device)
+        nd.valid_index(batch["padding_mask"])
+        real_lane = LANES.active(3)
+        # T lane: one call per forward pass, in the order the passes are issued on the host (per-module FIFO)
+        calls = [G, D, D, G, D] if real_lane else [G, D, G, D, D]
+        self._text_lane = nd.prefetch_text(calls, batch["bbox_text"], self.device)
+        if real_lane:
+            sR = LANES.fork("R", detached=True)
+            with torch.cuda.stream(sR):
+                D.requires_grad_(True)
+                D.text_encoder.requires_grad_(False)
+                self.flat["D"].zero_grad()
+                self._accumulate("Dreal", batch, None)
+                D.requires_grad_(False)
+                LANES.join_children()
+            self._real_lane = sR
+            self._real_issued = True
+
+    def _join_real_lane(self):
+        if self._real_lane is not None:
+            LANES.join(self._real_lane)
+            self._real_lane = None
+
+    def join_lanes(self):
+        """Bring every lane back into the current stream (end of the iteration / of a CUDA-graph segment)."""
+        if not self._lanes_on:
+            return
+        cur = torch.cuda.current_stream()
+        if self._text_lane is not None:
+            cur.wait_stream(self._text_lane)
+            self._text_lane = None
+        self._join_real_lane()
+        for m in (self.G, self.D):                   # results still queued are complete now: no event needed any more
+            for ent in m.__dict__.get("_te_queue", ()):
+                ent[1] = None
+        LANES.join_children()
+
+    def end_iteration(self):
+        if self._lanes_on:
+            self.join_lanes()
+            LANES.forget_children()
+            left = nd.pending_text((self.G, self.D))
+            if left:
+                for m in (self.G, self.D):
+                    m.__dict__["_te_queue"].clear()
+                raise RuntimeError("lane scheduler: %d prefetched text-encoder results were not consumed" % left)
+        if self._suspending:
+            LANES._suspended -= 1
+            self._suspending = False
+        self._iter_open = False
+        self._real_issued = False
+        self._warmed = True
 
     def iteration(self, batch, z_g, z_d, update_ema=True):
+        self.begin_iteration(batch)
         self._phase("G", batch, z_g)
         self._phase("D", batch, z_d)
         if update_ema:
@@ -91,11 +195,13 @@ class GraphedStep:
     def __init__(self, trainer):
         self.tr = trainer
         self.graphs = {}
+        self.stream = LANES.main_stream()          # warm-up + capture stream = the main lane
 
     def _key(self, host_batch):
         pm = host_batch["padding_mask"]
         G = self.tr.G
-        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup))
+        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup),
+                LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority)
 
     def _refresh_host_derived(self, st, host_mask):
         """Tokenise (host) into the front-ends' persistent device buffers and refresh the LM-loss normalisers."""
@@ -137,7 +243,8 @@ class GraphedStep:
             if n != "ema":
                 f.step = snap["steps"][n]
             E.bump_generation(f.params)
-        with torch.no_grad():                                    # cache misses -> shadows recomputed in place (stable pointers)
+        E.refresh_stale()                                        # shadows recomputed in place (stable pointers)
+        with torch.no_grad(), LANES.suspended():
             tr.G(st["z_g"], st["bbox_class"], st["bbox_real"], st["bbox_text"], st["bbox_patch"], st["padding_mask"],
                  st["background"], st["c"], reconst=True)
             tr.D(st["bbox_real"], st["bbox_class"], st["bbox_text"], st["bbox_patch"], st["padding_mask"], st["background"],
@@ -176,14 +283,16 @@ class GraphedStep:
             self._refresh_host_derived(st, host_batch["padding_mask"])
             # Warm-up + capture must not train: snapshot weights / Adam state / counters and restore them afterwards.
             snap = self._snapshot()
-            # warm up on a side stream (allocator pools, lazy inits, shadow caches reach their steady state), then capture
-            side = torch.cuda.Stream()
+            # warm up on the capture stream (allocator pools, lazy inits, shadow caches and the lane streams reach their
+            # steady state; the first iteration of a Trainer runs single-stream), then capture on the same stream
+            side = self.stream
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):
+                for _ in range(3 if not tr._warmed else 2):
                     tr.iteration(st, st["z_g"], st["z_d"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            tr.segmented = tr.num_gpus > 1
             from .. import _lib
             n0 = _lib.launch_count()
             if tr.num_gpus == 1:
@@ -196,13 +305,14 @@ class GraphedStep:
             graphs, pool = [], None
             for i, seg in enumerate(segs):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=pool, stream=side):
                     seg()
                 pool = g.pool()
                 graphs.append(g)
                 if tr.num_gpus > 1 and i < len(segs) - 1:       # keep the eager state consistent between captures
                     torch.cuda.synchronize()
             out = {ph: {k: v for k, v in terms.items()} for ph, terms in tr.loss.last.items()}
+            tr.segmented = False
             ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0)
             self.graphs[key] = ent
             self._restore(snap, st)

@@ -83,3 +83,35 @@ def test_data_parallel_gradient_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert ok and same
+
+
+def test_stream_cta_limit_table():
+    """ld_set_stream_cta_limit / ld_get_stream_cta_limit: per-stream cap, clamped to the SM count, cleared with <= 0."""
+    import ctypes
+    from layoutdetr_b200 import _lib
+    lib = _lib.lib()
+    s1, s2 = ctypes.c_void_p(0x1000), ctypes.c_void_p(0x2000)
+    full = lib.ld_get_stream_cta_limit(s1)
+    assert full >= 1
+    assert lib.ld_set_stream_cta_limit(s1, 100) == 0 and lib.ld_set_stream_cta_limit(s2, 7) == 0
+    assert lib.ld_get_stream_cta_limit(s1) == min(100, full) and lib.ld_get_stream_cta_limit(s2) == 7
+    assert lib.ld_set_stream_cta_limit(s1, 10 ** 6) == 0 and lib.ld_get_stream_cta_limit(s1) == full
+    lib.ld_set_stream_cta_limit(s1, 0)
+    lib.ld_set_stream_cta_limit(s2, -1)
+    assert lib.ld_get_stream_cta_limit(s1) == full and lib.ld_get_stream_cta_limit(s2) == full
+
+
+def test_engine_refresh_stale_recomputes_in_place():
+    """engine.refresh_stale: a derived shadow is recomputed into the SAME storage when its source changed."""
+    import torch
+    from layoutdetr_b200 import engine as E
+    p = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
+    v = E.derived((p,), "twice", lambda: (p.detach() * 2).clone())
+    ptr = v.data_ptr()
+    assert E.refresh_stale({id(p)}) == 0
+    with torch.no_grad():
+        p.add_(1.0)                       # bumps the version counter
+    assert E.refresh_stale({id(object())}) == 0       # not ours: left alone
+    assert E.refresh_stale({id(p)}) == 1
+    v2 = E.derived((p,), "twice", lambda: None)       # cache hit, no recompute
+    assert v2.data_ptr() == ptr and torch.equal(v2, (p.detach() * 2))
