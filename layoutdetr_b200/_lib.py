@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblayoutdetr_sm100.so")
+LIB_PATH = os.environ.get("LD_LIB_PATH_OVERRIDE") or os.path.join(_HERE, "liblayoutdetr_sm100.so")   # override: A/B of two builds
 _lib = None
 
 

@@ -152,8 +152,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // key blocks of this warp's half
         const int jb = half == 0 ? 0 : (p.nkv + 1) / 2;
         const int je = half == 0 ? (p.nkv + 1) / 2 : p.nkv;
-        float* xmax = xch;               // [2][128]
-        float* xsum = xch + 256;         // [2][128]
+        const uint32_t mask_a = smem_u32(mask_s);          // shared-space addresses (LDS / STS instead of generic LD / ST)
+        const uint32_t xmax_a = smem_u32(xch);             // [2][128]
+        const uint32_t xsum_a = xmax_a + 1024;             // [2][128]
+        const uint32_t p_a = smem_u32(p_s);
         mbar_wait(s_bar, 0);
         tc_fence_after();
         // ---- sweep 1: row max over this half's keys
@@ -165,17 +167,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld_x32(lane_addr + TM_S + 64 * j + 32 * hh, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = 64 * j + 32 * hh + i;
-                    float s = fmaf(__uint_as_float(v[i]), p.scale, mask_s[c]);
-                    if (p.causal && c > row) s += p.mask_value;
-                    mx = fmaxf(mx, s);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const int c4 = 64 * j + 32 * hh + 4 * i4;
+                    const float4 m4 = lds_f4(mask_a + c4 * 4);
+                    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c4 + u;
+                        float s = fmaf(__uint_as_float(v[4 * i4 + u]), p.scale, mm[u]);
+                        if (p.causal && c > row) s += p.mask_value;
+                        mx = fmaxf(mx, s);
+                    }
                 }
             }
         }
-        xmax[half * 128 + r] = mx;
+        sts_f32(xmax_a + (half * 128 + r) * 4, mx);
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        mx = fmaxf(xmax[r], xmax[128 + r]);
+        mx = fmaxf(lds_f32(xmax_a + r * 4), lds_f32(xmax_a + (128 + r) * 4));
         // ---- sweep 2: e = exp(s - max) -> bf16 into the swizzled A tile; fp32 row sum
         float sum = 0.f;
         for (int j = jb; j < je; ++j) {
@@ -186,30 +194,36 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld_wait();
                 float ev[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int c = 64 * j + 32 * hh + i;
-                    float s = fmaf(__uint_as_float(v[i]), p.scale, mask_s[c]);
-                    if (p.causal && c > row) s += p.mask_value;
-                    ev[i] = __expf(s - mx);
-                    sum += ev[i];
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const int c4 = 64 * j + 32 * hh + 4 * i4;
+                    const float4 m4 = lds_f4(mask_a + c4 * 4);
+                    const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c4 + u;
+                        float s = fmaf(__uint_as_float(v[4 * i4 + u]), p.scale, mm[u]);
+                        if (p.causal && c > row) s += p.mask_value;
+                        ev[4 * i4 + u] = __expf(s - mx);
+                        sum += ev[4 * i4 + u];
+                    }
                 }
-                uint8_t* prow = p_s + j * 16384 + r * 128;
+                const uint32_t prow_a = p_a + j * 16384 + r * 128;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {                    // four 16-byte pieces (8 keys each) of this 32-key run
                     uint4 o;
                     o.x = pack_bf16x2(ev[8 * g + 0], ev[8 * g + 1]); o.y = pack_bf16x2(ev[8 * g + 2], ev[8 * g + 3]);
                     o.z = pack_bf16x2(ev[8 * g + 4], ev[8 * g + 5]); o.w = pack_bf16x2(ev[8 * g + 6], ev[8 * g + 7]);
                     const int piece = hh * 4 + g;
-                    *reinterpret_cast<uint4*>(prow + ((piece ^ (r & 7)) << 4)) = o;
+                    sts_u4(prow_a + ((piece ^ (r & 7)) << 4), o);
                 }
             }
         }
-        xsum[half * 128 + r] = sum;
+        sts_f32(xsum_a + (half * 128 + r) * 4, sum);
         fence_proxy_async_smem();                                // generic-proxy smem writes -> visible to tcgen05.mma
         tc_fence_before();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (lane == 0) mbar_arrive(p_bar);
-        const float inv = __fdividef(1.0f, xsum[r] + xsum[128 + r]);
+        const float inv = __fdividef(1.0f, lds_f32(xsum_a + r * 4) + lds_f32(xsum_a + (128 + r) * 4));
         // ---- optional sweep 3: normalised probabilities to HBM (needed by the backward pass)
         if (p.P != nullptr) {
             __nv_bfloat16* prow_g = p.P + ((long)(b * p.H + h) * p.Lq + row) * p.ldp;
@@ -226,10 +240,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         const int c0 = 64 * j + 32 * hh + 8 * g;
                         if (c0 >= n_pad) continue;
                         float pe[8];
+                        const float4 ma = lds_f4(mask_a + c0 * 4), mb = lds_f4(mask_a + c0 * 4 + 16);
+                        const float mm[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int c = c0 + i;
-                            float s = fmaf(__uint_as_float(v[8 * g + i]), p.scale, mask_s[c]);
+                            float s = fmaf(__uint_as_float(v[8 * g + i]), p.scale, mm[i]);
                             if (p.causal && c > row) s += p.mask_value;
                             pe[i] = __expf(s - mx) * inv;
                         }
@@ -244,7 +260,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // ---- epilogue: O * (1 / sum) -> bf16, coalesced 64-byte row segments through a swizzled smem tile
         mbar_wait(o_bar, 0);
         tc_fence_after();
-        uint4* stg = reinterpret_cast<uint4*>(p_s) + e * 128;    // P tile is dead once the PV MMAs have retired
+        const uint32_t stg_a = p_a + e * 2048;                   // P tile is dead once the PV MMAs have retired
         const int sw_w = (lane >> 1) & 3, pc = lane & 3;
         const int cbeg = half * p.dch * 32, cend = cbeg + p.dch * 32;
         __nv_bfloat16* obase = p.O + (long)b * p.Lq * p.ldo + (long)h * p.d;
@@ -260,16 +276,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 o.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
                 o.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
                 o.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-                stg[lane * 4 + (g ^ sw_w)] = o;
+                sts_u4(stg_a + ((lane * 4 + (g ^ sw_w)) << 4), o);
             }
             __syncwarp();
+            uint4 val[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int rl = (lane >> 2) + 8 * i;
-                const uint4 val = stg[rl * 4 + (pc ^ ((rl >> 1) & 3))];
+                val[i] = lds_u4(stg_a + ((rl * 4 + (pc ^ ((rl >> 1) & 3))) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = (lane >> 2) + 8 * i;
                 const int grow = m0 + q * 32 + rl;
                 if (grow < p.Lq && c0 + pc * 8 < p.d)
-                    *reinterpret_cast<uint4*>(obase + (long)grow * p.ldo + c0 + pc * 8) = val;
+                    *reinterpret_cast<uint4*>(obase + (long)grow * p.ldo + c0 + pc * 8) = val[i];
             }
             __syncwarp();
         }

@@ -76,11 +76,54 @@ __device__ __forceinline__ float fast_erf(float x) {
 }
 
 // exact (erf) GELU as used by BERT "gelu" (reference training/med.py:301, ACT2FN['gelu'])
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f)); }
+// Same Abramowitz-Stegun form with the 1/sqrt(2) folded into the coefficients and the sign handled by
+//   gelu(x) = relu(x) - |0.5 x (1 - erf(|x| / sqrt 2))|        (x >= 0: x - q;  x < 0: q, with q = 0.5 x / t)
+// 6 FMA + 4 MUL + MUFU.RCP + 2 MUL + FMNMX + FADD = 15 issue slots per element (the GEMM epilogue is issue-bound here).
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float ax = fabsf(x);
+    float t = fmaf(5.3829750000e-06f, ax, 4.8890635643e-05f);
+    t = fmaf(t, ax, 3.8003575000e-05f);
+    t = fmaf(t, ax, 3.2776263241e-03f);
+    t = fmaf(t, ax, 2.1141006150e-02f);
+    t = fmaf(t, ax, 4.9867346967e-02f);
+    t = fmaf(t, ax, 1.0f);
+    t *= t; t *= t; t *= t; t *= t;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));      // t >= 1: no range fix-up needed
+    const float q = (0.5f * x) * r;
+    return fmaxf(x, 0.0f) - fabsf(q);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// explicit shared-space loads / stores (addresses from smem_u32).  Pointers derived from the 1024-byte-aligned
+// dynamic-smem base lose their address space in the compiler and would be accessed with GENERIC LD/ST (long-scoreboard
+// latency, LG queue) — measured as the epilogue bottleneck of gemm_bf16_kernel; these compile to LDS / STS.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

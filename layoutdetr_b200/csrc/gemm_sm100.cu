@@ -200,23 +200,35 @@ __device__ __forceinline__ void epilogue_generic_chunk(const KParams& p, const u
 }
 
 // Fast-path epilogue for 32 columns of one row: v = act(acc*alpha*cs + cb (+R)) * gain -> 128-bit stores.
+// cs_a / cb_a / stg_a are SHARED-space addresses (per-column scale / bias of this tile; this warp's 2 KB transpose buffer).
 template <int ACT, bool OUT_BF16, int RES>   // RES: 0 none, 1 bf16, 2 fp32
-__device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint32_t (&r)[32], float alpha, const float* cs_s,
-                                                    const float* cb_s, int c0, int n_base, long d_base, int row0, long r_off,
-                                                    uint4* stg) {
+__device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint32_t (&r)[32], float alpha, uint32_t cs_a,
+                                                    uint32_t cb_a, int c0, int n_base, long d_base, int row0, long r_off,
+                                                    uint32_t stg_a) {
+    // alpha is folded into the staged scale; for a linear epilogue without residual so is post_gain (scale and bias)
+    constexpr bool FOLD_GAIN = (ACT == LD_ACT_NONE && RES == 0);
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]) * alpha, cs_s[c0 + i], cb_s[c0 + i]);
+    for (int j = 0; j < 8; ++j) {
+        const float4 s4 = lds_f4(cs_a + (c0 + 4 * j) * 4);
+        const float4 b4 = lds_f4(cb_a + (c0 + 4 * j) * 4);
+        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), s4.x, b4.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
+    }
     if (RES == 1 && r_off >= 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base);
+        uint4 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = __ldg(rp + j);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint4 a = __ldg(rp + j);
             float lo, hi;
-            unpack_bf16x2(a.x, lo, hi); v[8 * j + 0] += lo; v[8 * j + 1] += hi;
-            unpack_bf16x2(a.y, lo, hi); v[8 * j + 2] += lo; v[8 * j + 3] += hi;
-            unpack_bf16x2(a.z, lo, hi); v[8 * j + 4] += lo; v[8 * j + 5] += hi;
-            unpack_bf16x2(a.w, lo, hi); v[8 * j + 6] += lo; v[8 * j + 7] += hi;
+            unpack_bf16x2(a[j].x, lo, hi); v[8 * j + 0] += lo; v[8 * j + 1] += hi;
+            unpack_bf16x2(a[j].y, lo, hi); v[8 * j + 2] += lo; v[8 * j + 3] += hi;
+            unpack_bf16x2(a[j].z, lo, hi); v[8 * j + 4] += lo; v[8 * j + 5] += hi;
+            unpack_bf16x2(a[j].w, lo, hi); v[8 * j + 6] += lo; v[8 * j + 7] += hi;
         }
     } else if (RES == 2 && r_off >= 0) {
         const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + r_off + n_base);
@@ -233,6 +245,7 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
     // Row-per-thread registers -> 32 x 64 B smem tile (XOR-swizzled 16 B pieces) -> each store instruction writes
     // eight 64 B row segments (full 32 B sectors) instead of 32 scattered 16 B pieces.
     const float gain = p.post_gain;
+#define LD_G(x) (FOLD_GAIN ? (x) : (x) * gain)
     const int lane = threadIdx.x & 31;
     const int sw_w = (lane >> 1) & 3;
     const int pc = lane & 3;
@@ -240,17 +253,22 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(v[8 * j + 0] * gain, v[8 * j + 1] * gain); o.y = pack_bf16x2(v[8 * j + 2] * gain, v[8 * j + 3] * gain);
-            o.z = pack_bf16x2(v[8 * j + 4] * gain, v[8 * j + 5] * gain); o.w = pack_bf16x2(v[8 * j + 6] * gain, v[8 * j + 7] * gain);
-            stg[lane * 4 + (j ^ sw_w)] = o;
+            o.x = pack_bf16x2(LD_G(v[8 * j + 0]), LD_G(v[8 * j + 1])); o.y = pack_bf16x2(LD_G(v[8 * j + 2]), LD_G(v[8 * j + 3]));
+            o.z = pack_bf16x2(LD_G(v[8 * j + 4]), LD_G(v[8 * j + 5])); o.w = pack_bf16x2(LD_G(v[8 * j + 6]), LD_G(v[8 * j + 7]));
+            sts_u4(stg_a + ((lane * 4 + (j ^ sw_w)) << 4), o);
         }
         __syncwarp();
         __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(p.D) + d_base + n_base + pc * 8;
+        uint4 val[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int rl = (lane >> 2) + 8 * i;
-            const uint4 val = stg[rl * 4 + (pc ^ ((rl >> 1) & 3))];
-            if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val;
+            val[i] = lds_u4(stg_a + ((rl * 4 + (pc ^ ((rl >> 1) & 3))) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = (lane >> 2) + 8 * i;
+            if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val[i];
         }
         __syncwarp();
     } else {
@@ -259,26 +277,33 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int b = 16 * h + 4 * j;
-                stg[lane * 4 + (j ^ sw_w)] = make_uint4(__float_as_uint(v[b] * gain), __float_as_uint(v[b + 1] * gain),
-                                                         __float_as_uint(v[b + 2] * gain), __float_as_uint(v[b + 3] * gain));
+                sts_u4(stg_a + ((lane * 4 + (j ^ sw_w)) << 4),
+                       make_uint4(__float_as_uint(LD_G(v[b])), __float_as_uint(LD_G(v[b + 1])),
+                                  __float_as_uint(LD_G(v[b + 2])), __float_as_uint(LD_G(v[b + 3]))));
             }
             __syncwarp();
             float* dbase = reinterpret_cast<float*>(p.D) + d_base + n_base + 16 * h + pc * 4;
+            uint4 val[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int rl = (lane >> 2) + 8 * i;
-                const uint4 val = stg[rl * 4 + (pc ^ ((rl >> 1) & 3))];
-                if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val;
+                val[i] = lds_u4(stg_a + ((rl * 4 + (pc ^ ((rl >> 1) & 3))) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rl = (lane >> 2) + 8 * i;
+                if (row0 + rl < p.M) *reinterpret_cast<uint4*>(dbase + (long)(row0 + rl) * p.ldd) = val[i];
             }
             __syncwarp();
         }
     }
 }
+#undef LD_G
 
 template <int ACT, bool OUT_BF16, int RES>
 __device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile& tl, uint32_t taddr, int col_begin, int col_end,
-                                                   bool row_ok, float alpha, const float* cs_s, const float* cb_s,
-                                                   long d_off, long r_off, long c_off, long d_base, int row0, uint4* stg) {
+                                                   bool row_ok, float alpha, uint32_t cs_a, uint32_t cb_a,
+                                                   long d_off, long r_off, long c_off, long d_base, int row0, uint32_t stg_a) {
     for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         const int n_base = tl.n0 + c0;
         if (n_base >= p.N) break;                       // warp-uniform
@@ -286,7 +311,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile&
         tmem_ld_x32(taddr + c0, r);
         tmem_ld_wait();
         if (n_base + 32 <= p.N) {                       // whole warp takes this branch together (transposed stores)
-            epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, r, alpha, cs_s, cb_s, c0, n_base, d_base, row0, row_ok ? r_off : -1, stg);
+            epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, r, alpha, cs_a, cb_a, c0, n_base, d_base, row0, row_ok ? r_off : -1, stg_a);
         } else if (row_ok) {                            // ragged last chunk of the matrix: scalar path
             uint32_t h[16];
 #pragma unroll
@@ -306,7 +331,7 @@ __device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile&
 // scale + mask + softmax + bf16 cast happen in the drain and the fp32 score matrix never reaches HBM.
 // Three sweeps over TMEM (max, sum, write); add_s = per-key additive mask staged in smem.
 __device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Tile& tl, uint32_t taddr, bool row_ok, int row,
-                                                      float scale, const float* add_s, long d_off) {
+                                                      float scale, uint32_t add_a, long d_off) {
     const int N = p.N;
     const int nch = (N + 31) >> 5;
     const float neg = p.mask_value;
@@ -318,7 +343,7 @@ __device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Ti
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int c = ch * 32 + i;
-            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            float v = fmaf(__uint_as_float(r[i]), scale, lds_f32(add_a + c * 4));
             if (p.causal && c > row) v += neg;
             if (c < N) mx = fmaxf(mx, v);
         }
@@ -331,7 +356,7 @@ __device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Ti
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int c = ch * 32 + i;
-            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            float v = fmaf(__uint_as_float(r[i]), scale, lds_f32(add_a + c * 4));
             if (p.causal && c > row) v += neg;
             if (c < N) sum += __expf(v - mx);
         }
@@ -347,7 +372,7 @@ __device__ __forceinline__ void epilogue_softmax_tile(const KParams& p, const Ti
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int c = ch * 32 + i;
-            float v = fmaf(__uint_as_float(r[i]), scale, add_s[c]);
+            float v = fmaf(__uint_as_float(r[i]), scale, lds_f32(add_a + c * 4));
             if (p.causal && c > row) v += neg;
             e[i] = (c < N) ? __expf(v - mx) * inv : 0.f;
         }
@@ -484,25 +509,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         const int q = e & 3;                          // TMEM lane quadrant of this warp (hardware: warp_id % 4)
         const int half = e >> 2;                      // which half of the tile's columns
         const int et = threadIdx.x - 128;             // 0..255 within the epilogue group
-        float* epi_s = reinterpret_cast<float*>(smem + PIPE_BYTES + BAR_BYTES);
+        const uint32_t epi_a = smem_u32(smem + PIPE_BYTES + BAR_BYTES);
         int as = 0; uint32_t aphase = 0;
         const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
+        const float fold_gain = (p.act == LD_ACT_NONE && !p.R) ? p.post_gain : 1.0f;     // see epilogue_fast_chunk
         const int col_begin = half * (p.bn >> 1), col_end = col_begin + (p.bn >> 1);
         for (int t = unit; t < p.total_tiles; t += nunits) {
             Tile tl = decode_tile(p, t);
             tl.m0 += (int)rank * BM;                  // this CTA's 128 rows of the (pair) tile
             const long c_off = (long)tl.b1 * p.col_sb1 + (long)tl.b2 * p.col_sb2;
-            float* cs_s = epi_s + as * 512;
-            float* cb_s = cs_s + 256;
+            const uint32_t cs_a = epi_a + as * 2048;  // shared-space addresses: [acc stage][scale | bias][256] fp32
+            const uint32_t cb_a = cs_a + 1024;
             if (p.softmax) {                          // stage the additive key mask of this batch
                 const uint8_t* km = p.key_mask ? p.key_mask + (long)tl.b1 * p.N : nullptr;
-                cs_s[et] = (km && et < p.N && km[et]) ? p.mask_value : 0.0f;
+                sts_f32(cs_a + et * 4, (km && et < p.N && km[et]) ? p.mask_value : 0.0f);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             } else if (p.fast) {                      // stage per-column scale / bias of this tile
                 const int n = tl.n0 + et;
                 const bool ok = et < p.bn && n < p.N;
-                cs_s[et] = (ok && p.cs) ? __ldg(p.cs + c_off + n) : 1.0f;
-                cb_s[et] = (ok && p.cb) ? __ldg(p.cb + c_off + n) : 0.0f;
+                sts_f32(cs_a + et * 4, ((ok && p.cs) ? __ldg(p.cs + c_off + n) : 1.0f) * alpha * fold_gain);
+                sts_f32(cb_a + et * 4, ((ok && p.cb) ? __ldg(p.cb + c_off + n) : 0.0f) * fold_gain);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(&tfull_bar[as], aphase);
@@ -514,11 +540,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
             const long d_base = (long)tl.b1 * p.d_sb1 + (long)tl.b2 * p.d_sb2;
             const int row0 = tl.m0 + q * 32;
-            uint4* stg = reinterpret_cast<uint4*>(smem + PIPE_BYTES + BAR_BYTES + EPI_STAGE_BYTES) + e * 128;
+            const uint32_t stg_a = epi_a + EPI_STAGE_BYTES + e * 2048;
             if (p.softmax) {
-                if (half == 0) epilogue_softmax_tile(p, tl, taddr, row_ok, row, alpha, cs_s, d_off);
+                if (half == 0) epilogue_softmax_tile(p, tl, taddr, row_ok, row, alpha, cs_a, d_off);
             } else if (p.fast) {
-#define LD_EPI(ACT, BF, RES) epilogue_fast_tile<ACT, BF, RES>(p, tl, taddr, col_begin, col_end, row_ok, alpha, cs_s, cb_s, d_off, r_off, c_off, d_base, row0, stg)
+#define LD_EPI(ACT, BF, RES) epilogue_fast_tile<ACT, BF, RES>(p, tl, taddr, col_begin, col_end, row_ok, alpha, cs_a, cb_a, d_off, r_off, c_off, d_base, row0, stg_a)
 #define LD_EPI_ACT(BF, RES)                                           \
                 switch (p.act) {                                      \
                     case LD_ACT_RELU:    LD_EPI(LD_ACT_RELU, BF, RES); break;    \

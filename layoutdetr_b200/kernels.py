@@ -80,10 +80,28 @@ class Out:
         return self.t.data_ptr() + self.t.element_size() * self.off
 
 
+GEMM_LOG = None        # tools/lane_trace.py sets this to a list: one (M, N, K, batches, a_mn, b_mn, split_k, caller) per launch
+
+
 def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0, accumulate=0, split_k=1,
          R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None, softmax=None):
     """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics."""
     _cuda(A.t, B.t, D.t)
+    if GEMM_LOG is not None:
+        import sys
+        f = sys._getframe(1)
+        names = []
+        while f is not None and len(names) < 4:
+            if f.f_code.co_name not in ("gemm", "linear", "apply", "_dgrad", "_wgrad") or len(names) == 0:
+                q = f.f_locals.get("ctx", None)
+                cls = type(f.f_locals["self"]).__name__ + "." if "self" in f.f_locals else ""
+                names.append(cls + f.f_code.co_name)
+            f = f.f_back
+        GEMM_LOG.append((M, N, K, nb1 * nb2, int(A.mn), int(B.mn), split_k, "<".join(names),
+                         dict(nb1=nb1, nb2=nb2, alpha=alpha, act=act, post_gain=post_gain, accumulate=accumulate, d_dtype=str(D.t.dtype),
+                              ldd=D.ld, d_sb=(D.sb1, D.sb2), a_ld=A.ld, a_sb=(A.sb1, A.sb2), b_ld=B.ld, b_sb=(B.sb1, B.sb2),
+                              r=None if R is None else (str(R.t.dtype), R.ld), cs=col_scale is not None, cb=col_bias is not None,
+                              aux=aux is not None, block_n=block_n, alpha_dev=alpha_dev is not None, softmax=softmax is not None)))
     d = _GemmDesc()
     d.M, d.N, d.K, d.nb1, d.nb2 = M, N, K, nb1, nb2
     d.act, d.accumulate, d.split_k = act, accumulate, split_k

@@ -40,9 +40,14 @@ from . import _lib
 class Lanes:
     def __init__(self):
         self.level = int(os.environ.get("LD_LANES", "3"))
-        self.text_ctas = int(os.environ.get("LD_LANE_TEXT_CTAS", "128"))       # grid cap of the text-encoder lane
-        self.lm_ctas = int(os.environ.get("LD_LANE_LM_CTAS", "128"))           # grid cap of the text-decoder branches
+        # grid caps of the tensor-bound lanes (0 = one CTA per SM).  Measured on B200 (profiles/r1_lane_sweep.txt): capping
+        # does not pay — the other lanes' kernels are short and get their SMs between the persistent GEMM's waves
+        self.text_ctas = int(os.environ.get("LD_LANE_TEXT_CTAS", "0"))         # text-encoder lane
+        self.lm_ctas = int(os.environ.get("LD_LANE_LM_CTAS", "0"))             # text-decoder branches
         self.high_priority = int(os.environ.get("LD_LANE_PRIORITY", "1"))      # latency-bound lanes outrank T / LM lanes
+        # dry run: the lane schedule's host-side issue order on ONE stream.  Results of a real multi-stream run must agree
+        # with it to fp32-accumulation noise — anything larger is a missing dependency between lanes (tests/test_lanes_gpu.py)
+        self.dry = int(os.environ.get("LD_LANES_DRY", "0"))
         self._streams = {}          # (device index, parent stream id, name) -> Stream
         self._children = {}         # parent stream id -> [child Stream]  (branches forked since the last join)
         self._suspended = 0
@@ -60,7 +65,7 @@ class Lanes:
         finally:
             self._suspended -= 1
 
-    def configure(self, level=None, text_ctas=None, lm_ctas=None, high_priority=None):
+    def configure(self, level=None, text_ctas=None, lm_ctas=None, high_priority=None, dry=None):
         """Change the schedule (drops the lane streams: their grid caps / priorities are fixed at creation)."""
         if level is not None:
             self.level = int(level)
@@ -70,6 +75,8 @@ class Lanes:
             self.lm_ctas = int(lm_ctas)
         if high_priority is not None:
             self.high_priority = int(high_priority)
+        if dry is not None:
+            self.dry = int(dry)
         for s in self._streams.values():
             _lib.lib().ld_set_stream_cta_limit(ctypes.c_void_p(s.cuda_stream), 0)
         self._streams.clear()
@@ -85,6 +92,8 @@ class Lanes:
     # -------------------------------------------------------------------------------------------- streams
     def _stream(self, name, cta_limit=0, bulk=False):
         cur = torch.cuda.current_stream()
+        if self.dry:
+            return cur
         key = (cur.device.index, cur.cuda_stream, name)
         s = self._streams.get(key)
         if s is None:
@@ -100,6 +109,8 @@ class Lanes:
         join_children: its owner joins it explicitly (T and R lanes)."""
         cur = torch.cuda.current_stream()
         s = self._stream(name, cta_limit, bulk)
+        if s is cur or s.cuda_stream == cur.cuda_stream:
+            return s
         s.wait_stream(cur)
         for t in tensors:
             if torch.is_tensor(t) and t.is_cuda:
@@ -114,6 +125,8 @@ class Lanes:
         """The current stream waits for lane `s`; `tensors` are the lane's results the current stream will read.  The lane
         stays registered: the backward pass runs on it again and join_children waits for it then."""
         cur = torch.cuda.current_stream()
+        if s.cuda_stream == cur.cuda_stream:
+            return
         cur.wait_stream(s)
         for t in tensors:
             if torch.is_tensor(t) and t.is_cuda:

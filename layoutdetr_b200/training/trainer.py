@@ -144,7 +144,8 @@ class Trainer:
             return
         cur = torch.cuda.current_stream()
         if self._text_lane is not None:
-            cur.wait_stream(self._text_lane)
+            if self._text_lane.cuda_stream != cur.cuda_stream:
+                cur.wait_stream(self._text_lane)
             self._text_lane = None
         self._join_real_lane()
         for m in (self.G, self.D):                   # results still queued are complete now: no event needed any more
@@ -201,7 +202,7 @@ class GraphedStep:
         pm = host_batch["padding_mask"]
         G = self.tr.G
         return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup),
-                LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority)
+                LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority, LANES.dry)
 
     def _refresh_host_derived(self, st, host_mask):
         """Tokenise (host) into the front-ends' persistent device buffers and refresh the LM-loss normalisers."""

@@ -21,8 +21,12 @@ def _small_models():
 
 def test_graph_replay_matches_eager():
     from layoutdetr_b200 import engine
+    from layoutdetr_b200.lanes import LANES
     from layoutdetr_b200.synthetic import make_inputs
     from layoutdetr_b200.training.trainer import Trainer, GraphedStep
+    # single-stream schedule: this test is about capture / replay (static buffers, device-side scalars, snapshot / restore);
+    # graph capture WITH lanes is pinned at gradient level by tests/test_lanes_gpu.py
+    LANES.configure(level=0)
     hb = [make_inputs(2, n_valid=8, seed=s) for s in (1, 2, 3)]
     zs = [torch.randn((2, 9, 4), device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)) for i in range(6)]
     results, losses = [], []
@@ -44,6 +48,7 @@ def test_graph_replay_matches_eager():
         torch.cuda.synchronize()
         losses.append(torch.stack(ls))
         results.append(tuple(f - i for f, i in zip((tr.flat["G"].p, tr.flat["D"].p, tr.flat_ema.p), init)))
+    LANES.configure(level=3)
     print("loss terms eager vs graph, max rel diff per iteration:",
           [float(((losses[0][i] - losses[1][i]).abs() / (losses[0][i].abs() + 1e-3)).max()) for i in range(3)])
     for i in range(3):

@@ -19,12 +19,12 @@ def _small_models():
     return nd.Generator(**kw_g).cuda(), nd.Discriminator(**kw_d).cuda()
 
 
-def _run(level, graph, iters=3):
+def _run(level, graph, iters=3, dry=0):
     from layoutdetr_b200 import engine
     from layoutdetr_b200.lanes import LANES
     from layoutdetr_b200.synthetic import make_inputs
     from layoutdetr_b200.training.trainer import Trainer, GraphedStep
-    LANES.configure(level=level, text_ctas=96, lm_ctas=96)
+    LANES.configure(level=level, text_ctas=96, lm_ctas=96, dry=dry)
     engine.clear_cache()
     G, D = _small_models()
     tr = Trainer(G, D, torch.device("cuda"), batch_size=2, lr=1e-5)
@@ -57,17 +57,20 @@ def test_lanes_match_single_stream(single_stream, level, graph):
     try:
         losses, upd = _run(level, graph)
     finally:
-        LANES.configure(level=3, text_ctas=128, lm_ctas=128)
+        LANES.configure(level=3, text_ctas=0, lm_ctas=0, dry=0)
     ref_losses, ref_upd = single_stream
     for it, (a, b) in enumerate(zip(losses, ref_losses)):
         assert set(a) == set(b)
         worst = max((abs(a[k] - b[k]) / (abs(b[k]) + 1e-3), k) for k in a)
         print("level", level, "graph", graph, "iter", it, "worst loss-term rel diff %.4g (%s)" % worst)
-        assert worst[0] < 5e-2, worst
+        assert worst[0] < (1e-3 if it == 0 else 0.1), worst      # iteration 0: same weights -> same forward
+    # The accumulated weight update is only reported: with the reference's Adam (beta1 = 0, eps = 1e-8) every parameter
+    # moves by +-lr whatever the size of its gradient, so bf16 summation-order differences on small gradients flip steps;
+    # the schedules are pinned at gradient level by test_lane_gradients_match_single_stream below.
     for ue, ur, name in zip(upd, ref_upd, ("G", "D")):
         rel = float((ue - ur).norm() / (ur.norm() + 1e-20))
         print("level", level, "graph", graph, name, "relative L2 difference of the accumulated update: %.4f" % rel)
-        assert rel < 0.15, (name, rel)      # Adam turns ~0 gradients (atomics-order noise) into +-lr steps; real bugs give O(1)
+        assert rel < 0.5, (name, rel)
 
 
 def test_stream_cta_limit_caps_the_gemm_grid():
@@ -86,3 +89,62 @@ def test_stream_cta_limit_caps_the_gemm_grid():
     torch.cuda.synchronize()
     _lib.lib().ld_set_stream_cta_limit(ctypes.c_void_p(s.cuda_stream), 0)
     assert torch.equal(out, ref)
+
+
+def _grads(level, graph, dry=0, loss_kwargs=None):
+    """Flat gradient buffers after the last iteration of a Trainer with lr = 0 (weights never move, so every schedule sees
+    the same forward; the first iteration of a Trainer is single-stream by design)."""
+    from layoutdetr_b200 import engine
+    from layoutdetr_b200.lanes import LANES
+    from layoutdetr_b200.synthetic import make_inputs
+    from layoutdetr_b200.training.trainer import Trainer, GraphedStep
+    LANES.configure(level=level, text_ctas=96, lm_ctas=96, dry=dry)
+    engine.clear_cache()
+    G, D = _small_models()
+    tr = Trainer(G, D, torch.device("cuda"), batch_size=2, lr=0.0, loss_kwargs=loss_kwargs)
+    hb = make_inputs(2, n_valid=8, seed=5)
+    zs = [torch.randn((2, 9, 4), device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)) for i in range(2)]
+    if graph:
+        gs = GraphedStep(tr)
+        gs.run(hb, zs[0], zs[1])
+        gs.run(hb, zs[0], zs[1])
+    else:
+        dev_b = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()}
+        for _ in range(3):
+            tr.iteration(dev_b, zs[0], zs[1])
+    torch.cuda.synchronize()
+    return tr.flat["G"].g.clone(), tr.flat["D"].g.clone()
+
+
+def _rel(a, b):
+    return [float((x - y).norm() / (y.norm() + 1e-20)) for x, y in zip(a, b)]
+
+
+def test_lane_gradients_match_single_stream():
+    """Race detector + parity of the schedules, on the flat gradient buffers of one iteration.
+
+    * Lanes on real streams vs the SAME issue order on one stream (dry run) must agree to fp32 atomics noise (1e-5) —
+      anything larger is a missing dependency between lanes.  This part runs with the background-reconstruction weight
+      at 0: with it on, D's gradients are only reproducible to ~1e-2 even run-to-run on ONE stream, because the
+      fp32 atomics of the style-gradient reduction (channel_dot) flip single bf16 roundings that the 8-layer mapping
+      network amplifies (measured: tools/debug_nondet.py); G's gradients stay at 1e-8 either way.
+    * Any schedule vs the single-stream one, full loss: G tight, D within that amplification bound (adds the order in
+      which autograd sums bf16 gradients meeting at the token output and the order of the two Dmain backward passes)."""
+    from layoutdetr_b200.lanes import LANES
+    nobg = dict(Dreal_im_rec_weight=0.0)
+    try:
+        ref = _grads(0, False)
+        ref_nobg = _grads(0, False, loss_kwargs=nobg)
+        print("single-stream run-to-run gradient noise (rel L2), no bg term: G %.3e  D %.3e"
+              % tuple(_rel(_grads(0, False, loss_kwargs=nobg), ref_nobg)))
+        for level in (1, 2, 3):
+            dry = _grads(level, False, dry=1, loss_kwargs=nobg)
+            for graph in (False, True) if level == 3 else (False,):
+                r_dry = _rel(_grads(level, graph, loss_kwargs=nobg), dry)
+                r_ref = _rel(_grads(level, graph), ref)
+                print("level %d graph %s: rel L2 vs dry run (no bg term) G %.3e D %.3e | vs single stream (full loss) G %.3e D %.3e"
+                      % (level, graph, r_dry[0], r_dry[1], r_ref[0], r_ref[1]))
+                assert max(r_dry) < 1e-5, (level, graph, r_dry)
+                assert r_ref[0] < 1e-5 and r_ref[1] < 5e-2, (level, graph, r_ref)
+    finally:
+        LANES.configure(level=3, text_ctas=0, lm_ctas=0, dry=0)

@@ -75,8 +75,11 @@ def main():
             torch.cuda.synchronize()
             terms = {ph + "/" + k: float(v.float().mean()) for ph in ("Gmain", "Dmain") for k, v in out[ph].items()}
             upd = {n: (tr.flat[n].p - p0[n]) for n in tr.flat}
+            grads = {n: tr.flat[n].g.clone() for n in tr.flat}            # gradients of the step just taken
             if ref is None:
-                ref = (terms, upd)
+                ref = (terms, upd, grads)
+            rec["grad_rel_l2_diff_vs_first"] = {n: float((grads[n] - ref[2][n]).norm() / (ref[2][n].norm() + 1e-20)) for n in grads}
+            rec["grad_max_abs_diff_vs_first"] = {n: float((grads[n] - ref[2][n]).abs().max()) for n in grads}
             rec["loss_max_rel_diff_vs_first"] = max(abs(terms[k] - ref[0][k]) / (abs(ref[0][k]) + 1e-3) for k in terms)
             rec["update_rel_l2_diff_vs_first"] = {n: float((upd[n] - ref[1][n]).norm() / (ref[1][n].norm() + 1e-20)) for n in upd}
             for _ in range(2):
