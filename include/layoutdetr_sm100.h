@@ -139,6 +139,13 @@ int ld_fma_f32(const float* a, const float* b, const float* c, float* y, const i
 int ld_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta,
                      void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
                      int rows, int C, float eps, void* stream);
+/* y = LayerNorm(x + res): the residual (bf16 rows, may be NULL) is added in fp32 before the statistics — the tail of a
+ * post-norm residual block (hidden = LayerNorm(dense(h) + input), training/med.py:237-242,321-325) when the dense output
+ * was stored as bf16. */
+int ld_layernorm_res_fwd(const void* x, int x_dtype, int64_t ldx, const void* res_bf16, int64_t ldr,
+                         const float* gamma, const float* beta,
+                         void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
+                         int rows, int C, float eps, void* stream);
 int ld_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
                      const float* mean, const float* rstd, const float* gamma,
                      void* dx_bf16, float* dx_f32, int64_t lddx, float* dgamma, float* dbeta,

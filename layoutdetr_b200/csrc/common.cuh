@@ -76,22 +76,22 @@ __device__ __forceinline__ float fast_erf(float x) {
 }
 
 // exact (erf) GELU as used by BERT "gelu" (reference training/med.py:301, ACT2FN['gelu'])
-// Same Abramowitz-Stegun form with the 1/sqrt(2) folded into the coefficients and the sign handled by
-//   gelu(x) = relu(x) - |0.5 x (1 - erf(|x| / sqrt 2))|        (x >= 0: x - q;  x < 0: q, with q = 0.5 x / t)
-// 6 FMA + 4 MUL + MUFU.RCP + 2 MUL + FMNMX + FADD = 15 issue slots per element (the GEMM epilogue is issue-bound here).
+// Same Abramowitz-Stegun form with 1/sqrt(2) and a factor 2^(1/16) folded into the coefficients (so that the 16th power
+// is 2 t and the reciprocal is 0.5 (1 - erf)) and the sign handled by
+//   gelu(x) = relu(x) - |x * 0.5 (1 - erf(|x| / sqrt 2))|        (x >= 0: x - q;  x < 0: q, with q = x / (2 t))
+// 6 FMA + 4 MUL + MUFU.RCP + MUL + FMNMX + FADD = 14 issue slots per element (the GEMM epilogue is issue-bound here).
 __device__ __forceinline__ float gelu_erf(float x) {
     const float ax = fabsf(x);
-    float t = fmaf(5.3829750000e-06f, ax, 4.8890635643e-05f);
-    t = fmaf(t, ax, 3.8003575000e-05f);
-    t = fmaf(t, ax, 3.2776263241e-03f);
-    t = fmaf(t, ax, 2.1141006150e-02f);
-    t = fmaf(t, ax, 4.9867346967e-02f);
-    t = fmaf(t, ax, 1.0f);
+    float t = fmaf(5.6212996640e-06f, ax, 5.1055209009e-05f);
+    t = fmaf(t, ax, 3.9686137011e-05f);
+    t = fmaf(t, ax, 3.4227392389e-03f);
+    t = fmaf(t, ax, 2.2076998457e-02f);
+    t = fmaf(t, ax, 5.2075163037e-02f);
+    t = fmaf(t, ax, 1.0442737824e+00f);
     t *= t; t *= t; t *= t; t *= t;
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));      // t >= 1: no range fix-up needed
-    const float q = (0.5f * x) * r;
-    return fmaxf(x, 0.0f) - fabsf(q);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));      // t >= 2: no range fix-up needed
+    return fmaxf(x, 0.0f) - fabsf(x * r);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));

@@ -43,6 +43,7 @@ struct KParams {
     int act, accumulate, split_k, d_dtype, r_dtype, bn;
     int a_mn, b_mn;
     int m_tiles, n_tiles, kb_total, kb_per_split, total_tiles;
+    uint32_t mg_split, mg_n, mg_m, mg_b2;   // magic multipliers ceil(2^32 / d) of the tile-index divisors (0: use '/')
     int tile_m;      // 128 (one CTA per tile) or 256 (CTA pair, cta_group::2)
     int vec_ok;
     int fast;        // compile-time specialised epilogue usable (aligned rows, store-only, no aux)
@@ -59,13 +60,22 @@ struct Tile {
     int b1, b2, m0, n0, kb_begin, kb_end;
 };
 
+// t / d and t % d with a host-validated multiply-high (integer division is ~25 instructions and every warp of the CTA
+// decodes every tile).
+__device__ __forceinline__ void divmod(int t, int d, uint32_t magic, int& q, int& r) {
+    if (d == 1) { q = t; r = 0; return; }
+    const int qq = magic ? (int)__umulhi((uint32_t)t, magic) : t / d;
+    const int rr = t - qq * d;          // (q may alias t)
+    q = qq; r = rr;
+}
+
 __device__ __forceinline__ Tile decode_tile(const KParams& p, int t) {
     Tile tl;
-    const int ks = t % p.split_k; t /= p.split_k;
-    const int nt = t % p.n_tiles; t /= p.n_tiles;
-    const int mt = t % p.m_tiles; t /= p.m_tiles;
-    tl.b2 = t % p.nb2;
-    tl.b1 = t / p.nb2;
+    int ks, nt, mt;
+    divmod(t, p.split_k, p.mg_split, t, ks);
+    divmod(t, p.n_tiles, p.mg_n, t, nt);
+    divmod(t, p.m_tiles, p.mg_m, t, mt);
+    divmod(t, p.nb2, p.mg_b2, tl.b1, tl.b2);
     tl.m0 = mt * p.tile_m;
     tl.n0 = nt * p.bn;
     tl.kb_begin = ks * p.kb_per_split;
@@ -206,7 +216,8 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
                                                     uint32_t cb_a, int c0, int n_base, long d_base, int row0, long r_off,
                                                     uint32_t stg_a) {
     // alpha is folded into the staged scale; for a linear epilogue without residual so is post_gain (scale and bias)
-    constexpr bool FOLD_GAIN = (ACT == LD_ACT_NONE && RES == 0);
+    // (relu / lrelu are positively homogeneous: act(g v) = g act(v) for g > 0); GELU epilogues never carry a gain (host check)
+    constexpr bool FOLD_GAIN = (RES == 0 && (ACT == LD_ACT_NONE || ACT == LD_ACT_RELU || ACT == LD_ACT_LRELU)) || ACT == LD_ACT_GELU;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -512,7 +523,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         const uint32_t epi_a = smem_u32(smem + PIPE_BYTES + BAR_BYTES);
         int as = 0; uint32_t aphase = 0;
         const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
-        const float fold_gain = (p.act == LD_ACT_NONE && !p.R) ? p.post_gain : 1.0f;     // see epilogue_fast_chunk
+        const float fold_gain = (!p.R && (p.act == LD_ACT_NONE || p.act == LD_ACT_RELU || p.act == LD_ACT_LRELU))
+                                    ? p.post_gain : 1.0f;                                 // see epilogue_fast_chunk
         const int col_begin = half * (p.bn >> 1), col_end = col_begin + (p.bn >> 1);
         for (int t = unit; t < p.total_tiles; t += nunits) {
             Tile tl = decode_tile(p, t);
@@ -676,6 +688,13 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     const long total = nb * p.m_tiles * p.n_tiles * p.split_k;
     LD_CHECK_ARG(total < (1L << 30), "gemm: too many tiles");
     p.total_tiles = (int)total;
+    auto magic = [total](int d) -> uint32_t {          // exact for every t < total iff t_max * (m*d - 2^32) < 2^32
+        if (d <= 1) return 0u;
+        const uint64_t m = ((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d;
+        const uint64_t e = m * (uint64_t)d - (1ull << 32);
+        return (m < (1ull << 32) && (uint64_t)total * e < (1ull << 32)) ? (uint32_t)m : 0u;
+    };
+    p.mg_split = magic(p.split_k); p.mg_n = magic(p.n_tiles); p.mg_m = magic(p.m_tiles); p.mg_b2 = magic(p.nb2);
 
     // vectorised epilogue needs 16-byte aligned rows for D / aux / R
     const int d_es = p.d_dtype == LD_BF16 ? 2 : 4;
@@ -690,6 +709,9 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     // fast epilogue: vector stores, plain store, no aux; activations only with bf16 output and non-fp32 residual
     p.fast = (p.vec_ok && p.accumulate == 0 && !p.aux &&
               (p.act == LD_ACT_NONE || (p.d_dtype == LD_BF16 && !(p.R && p.r_dtype == LD_F32)))) ? 1 : 0;
+    // the fast epilogue folds post_gain into the staged scale / bias: needs gain > 0 for relu / lrelu and gain == 1 for GELU
+    if ((p.act == LD_ACT_RELU || p.act == LD_ACT_LRELU) && !(p.post_gain > 0.0f)) p.fast = 0;
+    if (p.act == LD_ACT_GELU && p.post_gain != 1.0f) p.fast = 0;
 
     alignas(64) CUtensorMap tmA, tmB;
     int e = make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);

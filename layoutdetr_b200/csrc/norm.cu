@@ -36,7 +36,8 @@ template <> struct Vec4<__nv_bfloat16> {
 // training/detr_transformer.py:191-192,252-254; eps 1e-12 for BERT, 1e-5 for DETR)
 template <typename TIn>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-layernorm_fwd_kernel(const TIn* __restrict__ x, long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+layernorm_fwd_kernel(const TIn* __restrict__ x, long ldx, const __nv_bfloat16* __restrict__ res, long ldr,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y16, float* __restrict__ y32, long ldy,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int C, float eps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -50,6 +51,12 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, long ldx, const float* __restric
     for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
         if (j < chunks) {
             Vec4<TIn>::load(xr + (j * 32 + lane) * 4, v[j]);
+            if (res) {                                 // x + residual summed in fp32 (the post-norm residual block tail)
+                float rr[4];
+                Vec4<__nv_bfloat16>::load(res + row * ldr + (j * 32 + lane) * 4, rr);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[j][i] += rr[i];
+            }
             s += v[j][0] + v[j][1] + v[j][2] + v[j][3];
         }
     }
@@ -234,21 +241,29 @@ int check_ln(int rows, int C) {
 
 extern "C" {
 
-int ld_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta,
-                     void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
-                     int rows, int C, float eps, void* stream) {
+int ld_layernorm_res_fwd(const void* x, int x_dtype, int64_t ldx, const void* res_bf16, int64_t ldr,
+                         const float* gamma, const float* beta,
+                         void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
+                         int rows, int C, float eps, void* stream) {
     int e = check_ln(rows, C); if (e) return e;
     LD_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
-    LD_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0, "layernorm_fwd: ld must be a multiple of 4");
+    LD_CHECK_ARG(ldx % 4 == 0 && ldy % 4 == 0 && (!res_bf16 || ldr % 4 == 0), "layernorm_fwd: ld must be a multiple of 4");
     const int grid = ld::ceil_div(rows, LN_WARPS);
     cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* res = (const __nv_bfloat16*)res_bf16;
     if (x_dtype == LD_F32)
-        layernorm_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>((const float*)x, ldx, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, ldy, mean, rstd, rows, C, eps);
+        layernorm_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>((const float*)x, ldx, res, ldr, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, ldy, mean, rstd, rows, C, eps);
     else
-        layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, ldy, mean, rstd, rows, C, eps);
+        layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, res, ldr, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, ldy, mean, rstd, rows, C, eps);
     ld::count_launch();
     LD_LAUNCH_CHECK("layernorm_fwd");
     return 0;
+}
+
+int ld_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta,
+                     void* y_bf16, float* y_f32, int64_t ldy, float* mean, float* rstd,
+                     int rows, int C, float eps, void* stream) {
+    return ld_layernorm_res_fwd(x, x_dtype, ldx, nullptr, 0, gamma, beta, y_bf16, y_f32, ldy, mean, rstd, rows, C, eps, stream);
 }
 
 int ld_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,

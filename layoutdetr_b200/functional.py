@@ -20,6 +20,25 @@ def _needs(p):
     return p is not None and p.requires_grad
 
 
+_TRACK = [True]
+
+
+class _Fn(torch.autograd.Function):
+    """Base of the hand-written Functions.  `ctx.needs_input_grad` reports `requires_grad` of the inputs even under
+    `torch.no_grad()` (and grad mode is always off inside `forward`), so `apply` records the caller's grad mode and
+    `_need(ctx)` combines the two: a forward that will never be differentiated takes the inference path (fused activation
+    epilogues, no saved probabilities / pre-norm sums)."""
+
+    @classmethod
+    def apply(cls, *args):
+        _TRACK[0] = torch.is_grad_enabled()
+        return super().apply(*args)
+
+
+def _need(ctx):
+    return _TRACK[0] and any(ctx.needs_input_grad)
+
+
 def _wgrad(param, row0, row1, dy, x, alpha_dev=None):
     """param.grad[row0:row1, :Kin] += dy^T @ x   (dy [M, N] bf16, x [M, Kp] bf16)."""
     g = E.grad_buffer(param)
@@ -55,7 +74,7 @@ def pad_cols(x, mult=8):
     return K.cast_pad(x.contiguous(), torch.bfloat16, E.pad8(cols))
 
 
-class _CastPadFn(torch.autograd.Function):
+class _CastPadFn(_Fn):
     """fp32/bf16 [rows, cols] -> bf16 [rows, pad8(cols)] with gradient back to the source dtype."""
 
     @staticmethod
@@ -76,7 +95,7 @@ def to_bf16_padded(x):
     return _CastPadFn.apply(x)
 
 
-class _ToF32Fn(torch.autograd.Function):
+class _ToF32Fn(_Fn):
     @staticmethod
     def forward(ctx, x):
         return K.to_f32(x)
@@ -91,7 +110,7 @@ def to_f32(x):
 
 
 # ------------------------------------------------------------------------------------------------
-class LinearFn(torch.autograd.Function):
+class LinearFn(_Fn):
     """y = act(x @ W[row0:row1]^T + b[row0:row1] + residual) * post_gain, bf16 out."""
 
     @staticmethod
@@ -100,7 +119,7 @@ class LinearFn(torch.autograd.Function):
         b = bias.detach()[row0:row1] if bias is not None else None
         M = x.shape[0]
         N = row1 - row0
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need(ctx)
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
         aux = None
         if act == K.ACT_GELU and need_grad and (M * N) % 8 == 0:
@@ -146,7 +165,7 @@ def linear(x, weight, bias=None, act=K.ACT_NONE, residual=None, rows=None, post_
     return LinearFn.apply(x, residual, weight, bias, row0, row1, act, post_gain)
 
 
-class FusedLinearFn(torch.autograd.Function):
+class FusedLinearFn(_Fn):
     """y = x @ cat(W_0..W_n)^T + cat(b_0..b_n): several Linear layers sharing one input run as ONE GEMM
     (BERT query/key/value, training/med.py:109-116,157-180)."""
 
@@ -158,7 +177,7 @@ class FusedLinearFn(torch.autograd.Function):
         out = torch.empty((x.shape[0], w16.shape[0]), dtype=torch.bfloat16, device=x.device)
         K.linear(x, w16, b, out=out)
         ctx.ws, ctx.bs = ws, bs
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x)
         return out
 
@@ -186,18 +205,31 @@ def fused_linear(x, layers):
     return FusedLinearFn.apply(x, *args)
 
 
-class LinearLNFn(torch.autograd.Function):
+import os as _os
+LN_BF16_DENSE_NOGRAD = _os.environ.get("LD_LN_BF16_DENSE", "1") != "0"   # see LinearLNFn.forward
+
+
+class LinearLNFn(_Fn):
     """y = LayerNorm(x @ W^T + b + residual) — the post-norm residual block tail (BERT SelfOutput /
     Output: training/med.py:237-242,321-325; DETR: training/detr_transformer.py:210-214).  The pre-norm
-    sum stays fp32 inside the block."""
+    sum is formed in fp32.  When the block needs no gradient (frozen text encoder, inference) and the residual is bf16,
+    the dense output travels to the LayerNorm kernel as bf16 and the residual is added there (half the GEMM's store
+    traffic, and its plain bf16 epilogue instead of the fp32 + residual one); with gradients the fp32 sum is kept
+    for the backward pass."""
 
     @staticmethod
     def forward(ctx, x, residual, weight, bias, ln_w, ln_b, eps):
         w16 = E.w_bf16(weight)
         M, N = x.shape[0], weight.shape[0]
+        need_grad = _need(ctx)
+        if (LN_BF16_DENSE_NOGRAD and not need_grad and residual is not None and residual.dtype == torch.bfloat16
+                and residual.stride(1) == 1 and M * N >= (1 << 20)):
+            dense = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+            K.linear(x, w16, bias.detach() if bias is not None else None, out=dense)
+            y, _, _, _ = K.layernorm_fwd(dense, ln_w.detach(), ln_b.detach(), eps, residual=residual)
+            return y
         pre = torch.empty((M, N), dtype=torch.float32, device=x.device)
         K.linear(x, w16, bias.detach() if bias is not None else None, residual=residual, out=pre)
-        need_grad = any(ctx.needs_input_grad)
         y, _, mean, rstd = K.layernorm_fwd(pre, ln_w.detach(), ln_b.detach(), eps, save_stats=need_grad)
         ctx.weight, ctx.bias, ctx.ln_w, ctx.ln_b = weight, bias, ln_w, ln_b
         if need_grad:
@@ -223,10 +255,10 @@ def linear_ln(x, residual, weight, bias, ln_w, ln_b, eps):
     return LinearLNFn.apply(x, residual, weight, bias, ln_w, ln_b, eps)
 
 
-class LayerNormFn(torch.autograd.Function):
+class LayerNormFn(_Fn):
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, eps):
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need(ctx)
         y, _, mean, rstd = K.layernorm_fwd(x, ln_w.detach(), ln_b.detach(), eps, save_stats=need_grad)
         ctx.ln_w, ctx.ln_b = ln_w, ln_b
         if need_grad:
@@ -246,7 +278,7 @@ def layernorm(x, ln_w, ln_b, eps):
     return LayerNormFn.apply(x, ln_w, ln_b, eps)
 
 
-class AddBcastFn(torch.autograd.Function):
+class AddBcastFn(_Fn):
     """out = a + b with b broadcast over the leading dim of a (src + pos)."""
 
     @staticmethod
@@ -263,12 +295,12 @@ def add_bcast(a, b):
 
 
 # ------------------------------------------------------------------------------------------------
-class EmbedLNFn(torch.autograd.Function):
+class EmbedLNFn(_Fn):
     """BERT embeddings: LN(word[ids] + pos[t]) -> bf16 (training/med.py:74-97)."""
 
     @staticmethod
     def forward(ctx, ids, word, pos, ln_w, ln_b, T, eps, pad_id):
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need(ctx)
         y, pre, mean, rstd = K.embed_ln_fwd(ids, word.detach(), pos.detach(), ln_w.detach(), ln_b.detach(), T, eps, save=need_grad)
         ctx.params = (word, pos, ln_w, ln_b)
         ctx.T, ctx.pad_id = T, pad_id
@@ -292,7 +324,7 @@ class EmbedLNFn(torch.autograd.Function):
 FUSED_ATTENTION = True       # False -> batched-GEMM attention (QK^T with fused softmax epilogue, then PV); used by tests
 
 
-class AttentionFn(torch.autograd.Function):
+class AttentionFn(_Fn):
     """Multi-head attention core on projected buffers via batched tcgen05 GEMMs + masked softmax.
 
       S = (Q K^T) * scale (+ mask);  P = softmax(S);  O = P V        per (batch b, head h)
@@ -308,7 +340,7 @@ class AttentionFn(torch.autograd.Function):
         dev = q_t.device
         Lkp = E.pad8(Lk)
         ldq, ldk, ldv = q_t.stride(0), k_t.stride(0), v_t.stride(0)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need(ctx)
         ctx.dims = (q_off, k_off, v_off, B, H, Lq, Lk, d, scale)
         if Lk <= 256 and d <= 192 and d % 8 == 0 and FUSED_ATTENTION:
             # one kernel: QK^T -> mask/softmax -> PV; probabilities only go to HBM when the backward pass needs them
@@ -336,7 +368,7 @@ class AttentionFn(torch.autograd.Function):
         K.gemm(Lq, d, Lk, K.Op(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d, mn=True),
                K.Out(O, H * d, sb1=Lq * H * d, sb2=d), nb1=B, nb2=H)
         ctx.dims = (q_off, k_off, v_off, B, H, Lq, Lk, d, scale)
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(q_t, k_t, v_t, P)
         return O
 
@@ -389,7 +421,7 @@ def attention(q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale=None, k
 
 
 # ------------------------------------------------------------------------------------------------
-class LMHeadCEFn(torch.autograd.Function):
+class LMHeadCEFn(_Fn):
     """loss = mean over non-ignored rows of CE(h @ W_emb^T + b, labels; label_smoothing) — the tied
     30524-way LM head + loss (training/med.py:504-538, 910-920).  Logits live only as one bf16
     buffer that is overwritten in place by d(loss)/d(logits)."""
@@ -403,7 +435,7 @@ class LMHeadCEFn(torch.autograd.Function):
         buf = torch.empty((M, Vp), dtype=torch.bfloat16, device=h.device)
         logits = buf[:, :V]
         K.gemm(M, V, C, K.Op(h, h.stride(0)), K.Op(w16, w16.stride(0)), K.Out(buf, Vp), col_bias=bias.detach())
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need(ctx)
         # inv_n_valid: fp32 device scalar = 1 / #targets (device-side so a captured CUDA graph stays valid for any batch)
         loss_rows = K.cross_entropy(logits, labels, smoothing, -100, True, logits if need_grad else None, grad_scale=1.0,
                                     grad_scale_dev=inv_n_valid)
@@ -438,7 +470,7 @@ def lm_head_ce(h, emb_weight, bias, labels, inv_n_valid, smoothing=0.1):
     return LMHeadCEFn.apply(h, emb_weight, bias, labels, inv_n_valid, smoothing)
 
 
-class CrossEntropyFn(torch.autograd.Function):
+class CrossEntropyFn(_Fn):
     """Mean cross-entropy over rows (small heads: class logits, text-length logits)."""
 
     @staticmethod
@@ -472,7 +504,7 @@ def conv_weight_bf16(weight):
     return E.derived((weight,), "ohwi", make)
 
 
-class Conv2dFn(torch.autograd.Function):
+class Conv2dFn(_Fn):
     """y = act(conv(x, W) * scale + shift + residual) on channels-last bf16 activations.
 
     x: [B*H*W, Cin] bf16 (NHWC rows).  scale/shift: fp32 [Cout] (folded FrozenBatchNorm2d, reference
@@ -498,7 +530,7 @@ class Conv2dFn(torch.autograd.Function):
         ctx.weight, ctx.act, ctx.scale = weight, act, scale
         ctx.shift_param = shift if isinstance(shift, torch.nn.Parameter) else None
         ctx.has_res = residual is not None
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x, out if act != K.ACT_NONE else None)
         return out
 
@@ -551,7 +583,7 @@ def conv2d(x, weight, scale, shift, residual, B, H, W, stride, pad, act):
     return Conv2dFn.apply(x, weight, scale, shift, residual, (B, H, W, stride, pad), act)
 
 
-class MaxPool3s2Fn(torch.autograd.Function):
+class MaxPool3s2Fn(_Fn):
     @staticmethod
     def forward(ctx, x, B, H, W):
         C = x.shape[1]
@@ -573,7 +605,7 @@ def maxpool3s2(x, B, H, W):
 
 
 # ------------------------------------------------------------------------------------------------
-class LinearF32Fn(torch.autograd.Function):
+class LinearF32Fn(_Fn):
     """Head projection with fp32 output (boxes, logits): y = x @ W^T + b."""
 
     @staticmethod
@@ -582,7 +614,7 @@ class LinearF32Fn(torch.autograd.Function):
         out = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device)
         K.linear(x, w16, bias.detach() if bias is not None else None, out=out)
         ctx.weight, ctx.bias = weight, bias
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x)
         return out
 
@@ -606,7 +638,7 @@ def linear_f32(x, weight, bias=None):
     return LinearF32Fn.apply(x, weight, bias)
 
 
-class ScaledLinearFn(torch.autograd.Function):
+class ScaledLinearFn(_Fn):
     """StyleGAN2 FullyConnectedLayer: y = act(x @ (W * wg)^T + b * bg) * gain, bf16 or fp32 out
     (reference training/networks_stylegan2.py:92-126; lrelu gain sqrt(2) from bias_act.py:26)."""
 
@@ -620,7 +652,7 @@ class ScaledLinearFn(torch.autograd.Function):
         K.linear(x, w16, b, act=act, out=out, alpha=wg, post_gain=gain)
         ctx.cfg = (wg, bg, act, gain, out_f32)
         ctx.weight, ctx.bias = weight, bias
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x, out if act != K.ACT_NONE else None)
         return out
 
@@ -662,7 +694,7 @@ def scaled_linear(x, weight, bias, wg, bg, act=K.ACT_NONE, gain=1.0, out_f32=Fal
     return ScaledLinearFn.apply(x, weight, bias, wg, bg, act, gain, out_f32)
 
 
-class ScaleChannelsFn(torch.autograd.Function):
+class ScaleChannelsFn(_Fn):
     """y[b,p,c] = x[b,p,c] * s[b,c]  (style modulation of the activations, networks_stylegan2.py:67)."""
 
     @staticmethod
@@ -670,7 +702,7 @@ class ScaleChannelsFn(torch.autograd.Function):
         s = s.contiguous()
         y = K.scale_channels(x, s, torch.bfloat16, pixels * C, C)
         ctx.geom = (B, pixels, C)
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x, s)
         return y
 
@@ -688,7 +720,7 @@ def scale_channels(x, s, B, pixels, C):
     return ScaleChannelsFn.apply(x, s, B, pixels, C)
 
 
-class DemodBiasActFn(torch.autograd.Function):
+class DemodBiasActFn(_Fn):
     """y = act(x * d[b,c] + bias[c]) * gain on channels-last activations (demodulation + bias_act)."""
 
     @staticmethod
@@ -697,7 +729,7 @@ class DemodBiasActFn(torch.autograd.Function):
         y = K.demod_bias_act_fwd(x, dd, bias.detach() if bias is not None else None, B, pixels, C, act, gain)
         ctx.geom = (B, pixels, C, act, gain)
         ctx.bias = bias
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x, dd, y)
         return y
 
@@ -715,7 +747,7 @@ def demod_bias_act(x, d, bias, B, pixels, C, act, gain):
     return DemodBiasActFn.apply(x, d, bias, B, pixels, C, act, gain)
 
 
-class ConvTransposeUp2Fn(torch.autograd.Function):
+class ConvTransposeUp2Fn(_Fn):
     """Stride-2 transposed 3x3 convolution on channels-last bf16 (the `up=2` branch of conv2d_resample,
     torch_utils/ops/conv2d_resample.py:113-130): out[b, 2h+kh, 2w+kw, co] += x[b,h,w,ci] * W[co,ci,kh,kw].
     GEMM  cols = x @ Wt^T  ([B*H*W, 9*Cout], tcgen05)  followed by the gather-form col2im."""
@@ -739,7 +771,7 @@ class ConvTransposeUp2Fn(torch.autograd.Function):
         out = K.col2im(cols, B, Ho, Wo, Cout, H, W, KH, KW, 2, 0)
         ctx.geom = (B, H, W)
         ctx.weight = weight
-        if any(ctx.needs_input_grad):
+        if _need(ctx):
             ctx.save_for_backward(x)
         return out
 
@@ -767,7 +799,7 @@ def conv_transpose_up2(x, weight, B, H, W):
     return ConvTransposeUp2Fn.apply(x, weight, B, H, W)
 
 
-class UpfirdnNHWCFn(torch.autograd.Function):
+class UpfirdnNHWCFn(_Fn):
     """upfirdn2d on channels-last bf16 `[B*H*W, C]` activations; backward is another upfirdn2d with the
     flipped filter and up/down swapped (torch_utils/ops/upfirdn2d.py:248-270)."""
 

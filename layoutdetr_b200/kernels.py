@@ -156,17 +156,21 @@ def linear(x, w, bias=None, act=ACT_NONE, residual=None, out_dtype=torch.bfloat1
 
 
 # ------------------------------------------------------------------------------------------------
-def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=False):
+def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, out_f32=False, save_stats=False, residual=None):
+    """LayerNorm(x [+ residual]) over the last dim; residual (bf16, same shape) is added in fp32."""
     _cuda(x, gamma, beta)
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == x.shape and residual.stride(1) == 1
     rows, C = x.shape
     assert x.stride(1) == 1
     y16 = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if out_bf16 else None
     y32 = torch.empty((rows, C), dtype=torch.float32, device=x.device) if out_f32 else None
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
-    check(lib().ld_layernorm_fwd(_p(x), c_int(dt(x)), c_int64(x.stride(0)), _p(gamma), _p(beta), _p(y16), _p(y32),
-                                 c_int64(C), _p(mean), _p(rstd), c_int(rows), c_int(C), c_float(eps), _stream()),
-          "ld_layernorm_fwd")
+    check(lib().ld_layernorm_res_fwd(_p(x), c_int(dt(x)), c_int64(x.stride(0)), _p(residual),
+                                     c_int64(residual.stride(0) if residual is not None else 0), _p(gamma), _p(beta), _p(y16), _p(y32),
+                                     c_int64(C), _p(mean), _p(rstd), c_int(rows), c_int(C), c_float(eps), _stream()),
+          "ld_layernorm_res_fwd")
     return y16, y32, mean, rstd
 
 

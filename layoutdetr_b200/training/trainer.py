@@ -152,6 +152,7 @@ class Trainer:
             for ent in m.__dict__.get("_te_queue", ()):
                 ent[1] = None
         LANES.join_children()
+        LANES.forget_children()      # a later CUDA-graph segment must only wait for lanes it forked itself
 
     def end_iteration(self):
         if self._lanes_on:

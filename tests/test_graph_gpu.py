@@ -59,4 +59,8 @@ def test_graph_replay_matches_eager():
     for ue, ug, name in zip(results[0], results[1], ("G", "D", "G_ema")):
         rel = float((ue - ug).norm() / (ue.norm() + 1e-20))
         print(name, "relative L2 difference of the accumulated update, eager vs graph: %.4f" % rel)
-        assert rel < 0.15, (name, rel)          # Adam turns ~0 gradients (atomics-order noise) into +-lr steps; real bugs give O(1)
+        # Adam (beta1 = 0, eps = 1e-8) moves every parameter by +-lr whatever the size of its gradient: fp32-atomics-order
+        # noise flips the steps of ~0 gradients, and in D single bf16 roundings of the style gradients are amplified by the
+        # 8-layer mapping network (tools/debug_nondet.py) — run-to-run differences of 0.1-0.25 are normal here; a replay
+        # that read stale buffers gives uncorrelated updates (~1.4)
+        assert rel < 0.5, (name, rel)
