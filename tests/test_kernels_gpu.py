@@ -117,3 +117,21 @@ def test_cast_and_axpby():
     torch.testing.assert_close(out.float(), (a.float() + b[None]).to(torch.bfloat16).float(), atol=0, rtol=0)
     z = torch.randn((1024, 1024), generator=g, device="cuda")
     torch.testing.assert_close(k.to_bf16(z), z.to(torch.bfloat16), atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("C,KH,stride,pad,H", [(3, 7, 2, 3, 32), (5, 3, 1, 1, 9), (12, 3, 2, 1, 10), (16, 3, 1, 1, 8)])
+def test_im2col_matches_unfold(C, KH, stride, pad, H):
+    """Patch matrix of the conv path (ResNet stem 7x7/2 with C = 3 uses the gather kernel, C % 8 == 0 the vector one):
+    bit-exact against torch's unfold, K ordered (kh, kw, c), zero K-padding."""
+    import torch.nn.functional as F
+    from layoutdetr_b200 import kernels as K
+    B, W = 2, H + 3
+    x = torch.randn(B, C, H, W, device="cuda").to(torch.bfloat16)
+    rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+    cols, Ho, Wo = K.im2col(rows, B, H, W, C, KH, KH, stride, pad)
+    ref = F.unfold(x.float(), KH, padding=pad, stride=stride)                      # [B, C*KH*KW, L] with (c, kh, kw) order
+    ref = ref.view(B, C, KH * KH, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, KH * KH * C)
+    Kreal = KH * KH * C
+    assert cols.shape == (B * Ho * Wo, (Kreal + 7) // 8 * 8)
+    assert torch.equal(cols[:, :Kreal].float(), ref)
+    assert float(cols[:, Kreal:].float().abs().max()) == 0.0 if cols.shape[1] > Kreal else True
