@@ -143,7 +143,10 @@ def gemm_roofline(torch, K, pk):
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * M * N * Kd
     ach = flops / (ms * 1e-3) / 1e12
-    return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=None,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from the ncu --set full capture in
+    # profiles/r1_gemm_ncu_full_epilogue_variants.txt (61.5 MB read + 174.3 MB written; algorithmic: 61.3 + 226.5 MB, part of the
+    # output still sits in L2 when the kernel ends)
+    return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=235.7e6,
                 kernel="gemm_bf16_kernel", shape=[M, N, Kd], ms=ms, peak_source=pk["src"] + " burst (kernel timed alone)")
 
 
