@@ -99,8 +99,67 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
     }
 }
 
+// fp32, four consecutive elements per thread (128-bit accesses): usable when the bias is constant over groups of four
+// (stepB % 4 == 0, i.e. NCHW with H*W % 4 == 0, or no bias) and every pointer is 16-byte aligned.
+template <int A>
+__global__ void __launch_bounds__(256) bias_act_vec4_kernel(BiasActArgs p) {
+    const float4* x = (const float4*)p.x; const float* b = (const float*)p.b; const float4* xr = (const float4*)p.xref;
+    const float4* yr = (const float4*)p.yref; const float4* dyp = (const float4*)p.dy; float4* y = (float4*)p.y;
+    const int G = p.grad;
+    const long n4 = p.sizeX >> 2;
+    const float inv_gain = (p.gain != 0.f) ? 1.f / p.gain : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 xa = x[i];
+        const float bv = b ? __ldg(b + ((i * 4) / p.stepB) % p.sizeB) : 0.f;
+        const float4 xra = xr ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 yra = yr ? yr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dya = dyp ? dyp[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, xrs[4] = {xra.x, xra.y, xra.z, xra.w};
+        const float yrs[4] = {yra.x, yra.y, yra.z, yra.w}, dys[4] = {dya.x, dya.y, dya.z, dya.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float xv = xs[j], xref = xrs[j], yref = yrs[j];
+            const float yy = (p.gain != 0.f) ? yref / p.gain : 0.f;
+            (void)inv_gain;
+            if (G == 0) xv += bv; else xref += bv;
+            float out = bias_act_eval<A>(G, xv, xref, yy, p.alpha, yref, p.gain);
+            out *= p.gain * dys[j];
+            if (p.clamp >= 0.f) {
+                if (G == 0) out = (out > -p.clamp && out < p.clamp) ? out : (out >= 0.f ? p.clamp : -p.clamp);
+                else out = (yref > -p.clamp && yref < p.clamp) ? out : 0.f;
+            }
+            o[j] = out;
+        }
+        y[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <typename T> struct BiasActVec { static bool launch(const BiasActArgs&, cudaStream_t) { return false; } };
+template <> struct BiasActVec<float> {
+    static bool launch(const BiasActArgs& p, cudaStream_t st) {
+        auto al = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        if (p.sizeX % 4 != 0 || (p.b && p.stepB % 4 != 0) || !al(p.x) || !al(p.xref) || !al(p.yref) || !al(p.dy) || !al(p.y)) return false;
+        const int grid = ew_grid(p.sizeX / 4, 256);
+        switch (p.act) {
+            case 1: bias_act_vec4_kernel<1><<<grid, 256, 0, st>>>(p); break;
+            case 2: bias_act_vec4_kernel<2><<<grid, 256, 0, st>>>(p); break;
+            case 3: bias_act_vec4_kernel<3><<<grid, 256, 0, st>>>(p); break;
+            case 4: bias_act_vec4_kernel<4><<<grid, 256, 0, st>>>(p); break;
+            case 5: bias_act_vec4_kernel<5><<<grid, 256, 0, st>>>(p); break;
+            case 6: bias_act_vec4_kernel<6><<<grid, 256, 0, st>>>(p); break;
+            case 7: bias_act_vec4_kernel<7><<<grid, 256, 0, st>>>(p); break;
+            case 8: bias_act_vec4_kernel<8><<<grid, 256, 0, st>>>(p); break;
+            case 9: bias_act_vec4_kernel<9><<<grid, 256, 0, st>>>(p); break;
+            default: return false;
+        }
+        return true;
+    }
+};
+
 template <typename T>
 int launch_bias_act(const BiasActArgs& p, cudaStream_t st) {
+    if (BiasActVec<T>::launch(p, st)) return 0;
     const int grid = ew_grid(p.sizeX, 256);
     switch (p.act) {
         case 1: bias_act_kernel<T, 1><<<grid, 256, 0, st>>>(p); break;
@@ -164,6 +223,34 @@ __global__ void act_bwd_kernel(const TG* __restrict__ dy, const TR* __restrict__
     }
 }
 
+// bf16 x 8 per thread (n % 8 == 0, 16-byte aligned pointers)
+__global__ void __launch_bounds__(256) act_bwd_vec_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ref, uint4* __restrict__ dx,
+                                                          long n8, int act, float gain) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const uint4 ga = dy[i], ra = ref[i];
+        const uint32_t gw[4] = {ga.x, ga.y, ga.z, ga.w}, rw[4] = {ra.x, ra.y, ra.z, ra.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float g[2], r[2], d[2];
+            unpack_bf16x2(gw[j], g[0], g[1]); unpack_bf16x2(rw[j], r[0], r[1]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float gg = g[k] * gain;
+                switch (act) {
+                    case LD_ACT_RELU:    d[k] = r[k] > 0.f ? gg : 0.f; break;
+                    case LD_ACT_LRELU:   d[k] = r[k] > 0.f ? gg : 0.2f * gg; break;
+                    case LD_ACT_GELU:    d[k] = gg * gelu_erf_grad(r[k]); break;
+                    case LD_ACT_SIGMOID: { const float y = r[k] / gain; d[k] = gg * y * (1.f - y); } break;
+                    default:             d[k] = gg; break;
+                }
+            }
+            o[j] = pack_bf16x2(d[0], d[1]);
+        }
+        dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // y = act(x) * gain for activations that could not be fused into a GEMM epilogue (training-mode GELU keeps the
 // pre-activation as the GEMM output and applies the activation here)
 __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long n8, int act, float gain) {
@@ -219,12 +306,76 @@ __global__ void colsum_kernel(const T* __restrict__ x, long ld, float* __restric
     atomicAdd(out + c, s);
 }
 
+// bf16, eight columns per thread (128-bit loads), 8 row phases per block reduced through shared memory, 4 rows in flight
+// per thread: the scalar version issued one dependent 2-byte load per row per thread.
+__global__ void __launch_bounds__(256) colsum_vec8_kernel(const uint4* __restrict__ x, long ld8, float* __restrict__ out, long rows, int cols8,
+                                                          int rows_per_block) {
+    __shared__ float red[8][32][9];
+    const int cg = blockIdx.x * 32 + threadIdx.x;                 // column group (8 columns)
+    const long r0 = (long)blockIdx.y * rows_per_block;
+    const long r1 = min(rows, r0 + rows_per_block);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (cg < cols8) {
+        long r = r0 + threadIdx.y;
+        for (; r + 24 < r1; r += 32) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(x + (r + 8 * u) * ld8 + cg);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { float lo, hi; unpack_bf16x2(w[j], lo, hi); acc[2 * j] += lo; acc[2 * j + 1] += hi; }
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 v = __ldg(x + r * ld8 + cg);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float lo, hi; unpack_bf16x2(w[j], lo, hi); acc[2 * j] += lo; acc[2 * j + 1] += hi; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    const int t = threadIdx.y * 32 + threadIdx.x;                 // 256 threads -> 32 column groups x 8 columns
+    const int g = t >> 3, j = t & 7;
+    if (blockIdx.x * 32 + g < cols8) {
+        float s = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += red[y][g][j];
+        atomicAdd(out + (long)(blockIdx.x * 32 + g) * 8 + j, s);
+    }
+}
+
 // y[b, i, c] = x[b, i, c] * s[b, c]   (channels-last per-sample modulation; inner = C)
 template <typename TX, typename TO>
 __global__ void scale_channels_kernel(const TX* __restrict__ x, const float* __restrict__ s, TO* __restrict__ y, long n, long per_sample, int C) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const long b = i / per_sample; const int c = (int)(i % C);
         stf<TO>(y, i, ldf<TX>(x, i) * s[b * C + c]);
+    }
+}
+
+// bf16 -> bf16, eight channels per thread (C % 8 == 0, 16-byte aligned): 128-bit accesses, one index decode per vector
+__global__ void __launch_bounds__(256) scale_channels_vec_kernel(const uint4* __restrict__ x, const float* __restrict__ s, uint4* __restrict__ y,
+                                                                 long n8, long per_sample8, int C8) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / per_sample8; const int c8 = (int)(i % C8);
+        const float4* sp = reinterpret_cast<const float4*>(s + (b * C8 + c8) * 8);
+        const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const uint4 a = x[i];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float lo, hi; unpack_bf16x2(w[j], lo, hi);
+            o[j] = pack_bf16x2(lo * sc[2 * j], hi * sc[2 * j + 1]);
+        }
+        y[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -326,8 +477,11 @@ int ld_act_bwd(const void* dy, int dy_dtype, const void* ref, int ref_dtype, voi
                int64_t n, int act, float gain, void* stream) {
     LD_CHECK_ARG(dy && ref && dx && n > 0, "act_bwd: bad argument");
     LD_CHECK_ARG(dy_dtype == LD_BF16 && ref_dtype == LD_BF16 && dx_dtype == LD_BF16, "act_bwd: bf16 only");
-    act_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ref, (__nv_bfloat16*)dx, n, act, gain);
+    if (n % 8 == 0 && ((((uintptr_t)dy | (uintptr_t)ref | (uintptr_t)dx) & 15) == 0))
+        act_bwd_vec_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)ref, (uint4*)dx, n / 8, act, gain);
+    else
+        act_bwd_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)ref, (__nv_bfloat16*)dx, n, act, gain);
     ld::count_launch();
     LD_LAUNCH_CHECK("act_bwd");
     return 0;
@@ -353,6 +507,16 @@ int ld_act_fwd_bf16(const void* x, void* y, int64_t n, int act, float gain, void
 
 int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t rows, int cols, void* stream) {
     LD_CHECK_ARG(x && out && rows > 0 && cols > 0, "colsum: bad argument");
+    if (dtype == LD_BF16 && cols % 8 == 0 && ld_ % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+        const int gx = ld::ceil_div(cols / 8, 32);
+        const long want = std::max<long>(1, (long)ld::sm_count() * 4 / gx);          // ~4 blocks per SM in total
+        const int rpbv = (int)std::max<long>(32, (rows + want - 1) / want);
+        dim3 gridv(gx, (unsigned)ld::ceil_div((int)rows, rpbv));
+        colsum_vec8_kernel<<<gridv, dim3(32, 8), 0, (cudaStream_t)stream>>>((const uint4*)x, ld_ / 8, out, rows, cols / 8, rpbv);
+        ld::count_launch();
+        LD_LAUNCH_CHECK("colsum");
+        return 0;
+    }
     const int rpb = (int)std::max<long>(32, (rows + 255) / 256);
     dim3 grid(ld::ceil_div(cols, 128), ld::ceil_div(rows, rpb));
     if (dtype == LD_F32) colsum_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)x, ld_, out, rows, cols, rpb);
@@ -365,6 +529,12 @@ int ld_colsum_accum(const void* x, int dtype, int64_t ld_, float* out, int64_t r
 int ld_scale_channels(const void* x, int x_dtype, const float* s, void* y, int y_dtype, int64_t n, int64_t per_sample, int C, void* stream) {
     LD_CHECK_ARG(x && s && y && n > 0 && per_sample > 0 && C > 0 && per_sample % C == 0, "scale_channels: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == LD_BF16 && y_dtype == LD_BF16 && C % 8 == 0 && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) && (((uintptr_t)s) & 15) == 0) {
+        scale_channels_vec_kernel<<<ew_grid(n / 8, 256), 256, 0, st>>>((const uint4*)x, s, (uint4*)y, n / 8, per_sample / 8, C / 8);
+        ld::count_launch();
+        LD_LAUNCH_CHECK("scale_channels");
+        return 0;
+    }
     const int grid = ew_grid(n, 256);
     if (x_dtype == LD_BF16 && y_dtype == LD_BF16) scale_channels_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, s, (__nv_bfloat16*)y, n, per_sample, C);
     else if (x_dtype == LD_F32 && y_dtype == LD_BF16) scale_channels_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)x, s, (__nv_bfloat16*)y, n, per_sample, C);
@@ -396,6 +566,47 @@ __global__ void demod_bias_act_fwd_kernel(const TX* __restrict__ x, const float*
         if (bias) v += bias[c];
         if (act == LD_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
         y[i] = f32_to_bf16(v * gain);
+    }
+}
+
+// bf16 x, eight channels per thread (C % 8 == 0, 16-byte aligned)
+__global__ void __launch_bounds__(256)
+demod_bias_act_fwd_vec_kernel(const uint4* __restrict__ x, const float* __restrict__ d, const float* __restrict__ bias,
+                              uint4* __restrict__ y, long n8, long per_sample8, int C8, int act, float gain) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / per_sample8; const int c8 = (int)(i % C8);
+        float dc[8], bc[8];
+        if (d) {
+            const float4* dp = reinterpret_cast<const float4*>(d + (b * C8 + c8) * 8);
+            const float4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+            dc[0] = d0.x; dc[1] = d0.y; dc[2] = d0.z; dc[3] = d0.w; dc[4] = d1.x; dc[5] = d1.y; dc[6] = d1.z; dc[7] = d1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dc[j] = 1.f;
+        }
+        if (bias) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + c8 * 8);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            bc[0] = b0.x; bc[1] = b0.y; bc[2] = b0.z; bc[3] = b0.w; bc[4] = b1.x; bc[5] = b1.y; bc[6] = b1.z; bc[7] = b1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bc[j] = 0.f;
+        }
+        const uint4 a = x[i];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[2]; unpack_bf16x2(w[j], v[0], v[1]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float t = fmaf(v[k], dc[2 * j + k], bc[2 * j + k]);
+                if (act == LD_ACT_LRELU) t = t > 0.f ? t : 0.2f * t;
+                v[k] = t * gain;
+            }
+            o[j] = pack_bf16x2(v[0], v[1]);
+        }
+        y[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -522,6 +733,14 @@ int ld_demod_bias_act_fwd(const void* x, int x_dtype, const float* d, const floa
                           int B, int64_t pixels, int C, int act, float gain, void* stream) {
     LD_CHECK_ARG(x && y_bf16 && B > 0 && pixels > 0 && C > 0, "demod_bias_act_fwd: bad argument");
     const long n = (long)B * pixels * C;
+    if (x_dtype == LD_BF16 && C % 8 == 0 && ((((uintptr_t)x | (uintptr_t)y_bf16) & 15) == 0) &&
+        (!d || ((uintptr_t)d & 15) == 0) && (!bias || ((uintptr_t)bias & 15) == 0)) {
+        demod_bias_act_fwd_vec_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const uint4*)x, d, bias, (uint4*)y_bf16, n / 8, pixels * C / 8, C / 8, act, gain);
+        ld::count_launch();
+        LD_LAUNCH_CHECK("demod_bias_act_fwd");
+        return 0;
+    }
     const int grid = ew_grid(n, 256);
     if (x_dtype == LD_F32) demod_bias_act_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, d, bias, (__nv_bfloat16*)y_bf16, n, pixels * C, C, act, gain);
     else demod_bias_act_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, d, bias, (__nv_bfloat16*)y_bf16, n, pixels * C, C, act, gain);

@@ -48,6 +48,7 @@ class Lanes:
         # dry run: the lane schedule's host-side issue order on ONE stream.  Results of a real multi-stream run must agree
         # with it to fp32-accumulation noise — anything larger is a missing dependency between lanes (tests/test_lanes_gpu.py)
         self.dry = int(os.environ.get("LD_LANES_DRY", "0"))
+        self.real_first = int(os.environ.get("LD_LANE_REAL_FIRST", "0"))       # T-lane order: real-sample D pass's call first
         self._streams = {}          # (device index, parent stream id, name) -> Stream
         self._children = {}         # parent stream id -> [child Stream]  (branches forked since the last join)
         self._suspended = 0
@@ -65,7 +66,7 @@ class Lanes:
         finally:
             self._suspended -= 1
 
-    def configure(self, level=None, text_ctas=None, lm_ctas=None, high_priority=None, dry=None):
+    def configure(self, level=None, text_ctas=None, lm_ctas=None, high_priority=None, dry=None, real_first=None):
         """Change the schedule (drops the lane streams: their grid caps / priorities are fixed at creation)."""
         if level is not None:
             self.level = int(level)
@@ -77,6 +78,8 @@ class Lanes:
             self.high_priority = int(high_priority)
         if dry is not None:
             self.dry = int(dry)
+        if real_first is not None:
+            self.real_first = int(real_first)
         for s in self._streams.values():
             _lib.lib().ld_set_stream_cta_limit(ctypes.c_void_p(s.cuda_stream), 0)
         self._streams.clear()

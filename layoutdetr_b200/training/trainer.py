@@ -120,6 +120,8 @@ class Trainer:
         real_lane = LANES.active(3)
         # T lane: one call per forward pass, in the order the passes are issued on the host (per-module FIFO)
         calls = [G, D, D, G, D] if real_lane else [G, D, G, D, D]
+        if real_lane and LANES.real_first:           # feed the R lane (the longest chain) before Gmain
+            calls = [D, G, D, G, D]
         self._text_lane = nd.prefetch_text(calls, batch["bbox_text"], self.device)
         if real_lane:
             sR = LANES.fork("R", detached=True)
@@ -203,7 +205,7 @@ class GraphedStep:
         pm = host_batch["padding_mask"]
         G = self.tr.G
         return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup),
-                LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority, LANES.dry)
+                LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority, LANES.dry, LANES.real_first)
 
     def _refresh_host_derived(self, st, host_mask):
         """Tokenise (host) into the front-ends' persistent device buffers and refresh the LM-loss normalisers."""

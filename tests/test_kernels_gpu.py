@@ -135,3 +135,45 @@ def test_im2col_matches_unfold(C, KH, stride, pad, H):
     assert cols.shape == (B * Ho * Wo, (Kreal + 7) // 8 * 8)
     assert torch.equal(cols[:, :Kreal].float(), ref)
     assert float(cols[:, Kreal:].float().abs().max()) == 0.0 if cols.shape[1] > Kreal else True
+
+
+def test_vectorised_elementwise_kernels_match_torch():
+    """128-bit paths of the bytes-bound kernels (column sums, per-sample channel scaling, activation backward,
+    demodulation + bias + leaky ReLU, fp32 bias_act) against plain fp32 torch math."""
+    from layoutdetr_b200 import kernels as K
+    from layoutdetr_b200.torch_utils.ops import bias_act as ba
+    torch.manual_seed(0)
+    B, P, C = 3, 37, 48
+    x = torch.randn(B * P, C, device="cuda").to(torch.bfloat16)
+    # column sums (rows not a multiple of the row tiling), accumulated onto existing values, on a strided column slice
+    big = torch.randn(1000, 96, device="cuda").to(torch.bfloat16)
+    out = torch.ones(48, device="cuda")
+    K.colsum_accum(big[:, 48:], out)
+    torch.testing.assert_close(out, 1.0 + big[:, 48:].float().sum(0), rtol=1e-5, atol=1e-3)
+    # y[b, p, c] = x[b, p, c] * s[b, c]
+    s = torch.randn(B, C, device="cuda")
+    y = K.scale_channels(x, s, torch.bfloat16, P * C, C)
+    ref = (x.float().view(B, P, C) * s[:, None, :]).view(B * P, C)
+    torch.testing.assert_close(y.float(), ref.to(torch.bfloat16).float())
+    # activation backward (leaky ReLU with gain, exact GELU)
+    dy = torch.randn(B * P, C, device="cuda").to(torch.bfloat16)
+    d = K.act_bwd(dy, x, K.ACT_LRELU, 2 ** 0.5).float()
+    ref = dy.float() * 2 ** 0.5 * torch.where(x.float() > 0, 1.0, 0.2)
+    torch.testing.assert_close(d, ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    d = K.act_bwd(dy, x, K.ACT_GELU).float()
+    xf = x.float().requires_grad_(True)
+    torch.nn.functional.gelu(xf).backward(dy.float())
+    torch.testing.assert_close(d, xf.grad.to(torch.bfloat16).float(), rtol=2e-2, atol=2e-2)
+    # demodulation + bias + leaky ReLU * gain
+    dc = torch.rand(B, C, device="cuda") + 0.5
+    bias = torch.randn(C, device="cuda")
+    y = K.demod_bias_act_fwd(x, dc, bias, B, P, C, K.ACT_LRELU, 2 ** 0.5).float()
+    ref = torch.nn.functional.leaky_relu(x.float().view(B, P, C) * dc[:, None, :] + bias, 0.2).view(B * P, C) * 2 ** 0.5
+    torch.testing.assert_close(y, ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    # fp32 bias_act, NCHW with H*W % 4 == 0 (vector path) and % 4 != 0 (scalar path)
+    for hw in ((8, 8), (5, 7)):
+        img = torch.randn(2, 6, *hw, device="cuda")
+        b6 = torch.randn(6, device="cuda")
+        got = ba.bias_act(img, b6, act="lrelu", gain=1.5, clamp=2.0)
+        ref = (torch.nn.functional.leaky_relu(img + b6[None, :, None, None], 0.2) * 1.5).clamp(-2.0, 2.0)
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)

@@ -56,9 +56,10 @@ def main():
         text_ctas = parts[1] if len(parts) > 1 else 128
         lm_ctas = parts[2] if len(parts) > 2 else 128
         prio = parts[3] if len(parts) > 3 else 1
-        LANES.configure(level=level, text_ctas=text_ctas, lm_ctas=lm_ctas, high_priority=prio)
+        real_first = parts[4] if len(parts) > 4 else 0
+        LANES.configure(level=level, text_ctas=text_ctas, lm_ctas=lm_ctas, high_priority=prio, real_first=real_first)
         gs = GraphedStep(tr)
-        rec = dict(level=level, text_ctas=text_ctas, lm_ctas=lm_ctas, priority=prio)
+        rec = dict(level=level, text_ctas=text_ctas, lm_ctas=lm_ctas, priority=prio, real_first=real_first)
         try:
             if base_snap is None:
                 # one throw-away capture brings every cache to its steady state; then remember the weights
