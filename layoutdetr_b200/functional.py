@@ -460,9 +460,10 @@ class LMHeadCEFn(_Fn):
         if _needs(ctx.emb_weight):
             _wgrad(ctx.emb_weight, 0, V, dl, h, alpha_dev=g)
         if _needs(ctx.bias):
-            tmp = torch.zeros(V, dtype=torch.float32, device=h.device)
-            K.colsum_accum(dl, tmp)
-            E.grad_buffer(ctx.bias).add_(tmp * g)
+            # sum over the padded width (128-bit path); the pad columns of `buf` are never written and are dropped here
+            tmp = torch.zeros(buf.shape[1], dtype=torch.float32, device=h.device)
+            K.colsum_accum(buf, tmp)
+            E.grad_buffer(ctx.bias).add_(tmp[:V] * g)
         return dh, None, None, None, None, None
 
 
@@ -789,8 +790,10 @@ class ConvTransposeUp2Fn(_Fn):
             dx = _dgrad(dcols, wt, wt.shape[1])
         if _needs(weight):
             M = dcols.shape[0]
-            tmp = torch.empty((KH * KW * Cout, Cin), dtype=torch.float32, device=x.device)
-            K.gemm(KH * KW * Cout, Cin, M, K.Op(dcols, dcols.stride(0), mn=True), K.Op(x, x.stride(0), mn=True), K.Out(tmp, Cin))
+            sk = E.wgrad_split_k(KH * KW * Cout, Cin, M)       # few output tiles, reduction over every pixel: split K
+            tmp = (torch.zeros if sk > 1 else torch.empty)((KH * KW * Cout, Cin), dtype=torch.float32, device=x.device)
+            K.gemm(KH * KW * Cout, Cin, M, K.Op(dcols, dcols.stride(0), mn=True), K.Op(x, x.stride(0), mn=True), K.Out(tmp, Cin),
+                   accumulate=2 if sk > 1 else 0, split_k=sk)
             E.grad_buffer(weight).add_(tmp.view(KH, KW, Cout, Cin).permute(2, 3, 0, 1))
         return dx, None, None, None, None
 

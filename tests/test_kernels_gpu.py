@@ -177,3 +177,21 @@ def test_vectorised_elementwise_kernels_match_torch():
         got = ba.bias_act(img, b6, act="lrelu", gain=1.5, clamp=2.0)
         ref = (torch.nn.functional.leaky_relu(img + b6[None, :, None, None], 0.2) * 1.5).clamp(-2.0, 2.0)
         torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("C,with_res", [(768, True), (256, True), (768, False), (384, True)])
+def test_layernorm_residual_forward(C, with_res):
+    """LayerNorm(x + residual) on bf16 rows (128-bit path for C % 256 == 0, generic path otherwise) vs fp32 torch."""
+    from layoutdetr_b200 import kernels as k
+    torch.manual_seed(1)
+    rows = 133
+    x = torch.randn(rows, C, device="cuda").to(torch.bfloat16)
+    res = torch.randn(rows, C, device="cuda").to(torch.bfloat16) if with_res else None
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    y, _, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-12, save_stats=True, residual=res)
+    pre = x.float() + (res.float() if with_res else 0.0)
+    ref = torch.nn.functional.layer_norm(pre, (C,), gamma, beta, 1e-12)
+    torch.testing.assert_close(y.float(), ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(mean, pre.mean(1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rstd, (pre.var(1, unbiased=False) + 1e-12).rsqrt(), rtol=1e-4, atol=1e-5)
