@@ -102,7 +102,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = 1
+    B = max(1, args.cpu_sample)
     times = []
     for i in range(args.warmup_ref + args.steps_ref):
         t = cpu_iteration_seconds(B, threads)
@@ -169,7 +169,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()        # fail loudly if the CUDA library is missing
     pk = peaks()
-    B = args.batch
+    B = args.batch                                # weak scaling: 16 samples on every GPU
+    if args.scaling == "strong":                  # the reference's `--batch=16 --gpus=N`: the 16 samples are split over the ranks
+        assert args.batch % world == 0, "strong scaling needs batch % gpus == 0"
+        B = args.batch // world
 
     torch.manual_seed(0)                          # identical initial weights on every rank (reference broadcasts from rank 0)
     G = nd.Generator(**G_KWARGS).to(dev)
@@ -303,11 +306,12 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sec = cpu_iteration_seconds(1, threads)
-            cpu = dict(value=1.0 / sec, unit="samples/s", cores=threads, kind="port",
-                       sample="1 sample: oracle Gmain+Dmain fwd+bwd, dense T=256, fp32 (%.1f s)" % sec)
+            nb = max(1, args.cpu_sample)
+            sec = cpu_iteration_seconds(nb, threads)
+            cpu = dict(value=nb / sec, unit="samples/s", cores=threads, kind="port",
+                       sample="%d samples in one batch: oracle Gmain+Dmain fwd+bwd, dense T=256, fp32 (%.1f s)" % (nb, sec))
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload="bs16 256x256 synthetic, 8 of 9 slots, G+D fwd/bwd + Adam + EMA (BASELINE configs[1])",
                                 batch_per_gpu=B, global_batch=B * world, text_tokens=256, text_trim=bool(args.text_trim),
                                 text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
@@ -328,7 +332,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch samples on every GPU (default); strong: --batch samples split over the GPUs (reference --batch=16 semantics)")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="samples in the bounded CPU-baseline step")
     ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
     ap.add_argument("--graph", type=int, default=1, help="1: capture the iteration into a CUDA graph (single-GPU default)")

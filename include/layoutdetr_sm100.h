@@ -221,6 +221,24 @@ int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
                      float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Layout box losses of the generator objective, value + analytic gradient, one launch each.  Replace the eager
+ * elementwise chains of metrics/metric_layoutnet.py: compute_overlap :153-179, compute_alignment :182-201,
+ * generalized_iou_loss :245-275 (called from training/loss.py:117-125) and their autograd backward.
+ *
+ * ld_layout_losses: bbox [B, N, 4] fp32 (xc, yc, w, h), valid [B, N] bytes (1 = real element, i.e. ~padding_mask),
+ *   1 <= N <= 64.  overlap[b] = sum_{i != j} area(i n j) / area(i) / n_valid (invalid boxes zeroed first);
+ *   alignment[b] = sum_i -log(1 - min_{c, j != i} |X_c,i - X_c,j|) / n_valid over the six edge / centre coordinates
+ *   (a minimum of exactly 1 counts as 0).  j_overlap / j_alignment (optional, [B, N, 4]) receive
+ *   d overlap[b] / d bbox[b] and d alignment[b] / d bbox[b] with autograd's conventions (ties of max / min split
+ *   evenly, first minimum takes the gradient, nan_to_num / masked_fill stop it).
+ * ld_giou_loss: fake, real [M, 4]; loss[0] = mean_m (1 - GIoU(fake_m, real_m)); j_fake (optional) = d loss / d fake.
+ * ld_rows_scale: out[i] (+)= J[i] * g[i / per] — the chain rule through a stored Jacobian (g: [B] or one scalar). */
+int ld_layout_losses(const float* bbox, const uint8_t* valid, int64_t B, int N, float* overlap, float* alignment,
+                     float* j_overlap, float* j_alignment, void* stream);
+int ld_giou_loss(const float* fake, const float* real, int64_t M, float* loss, float* j_fake, void* stream);
+int ld_rows_scale(const float* J, const float* g, float* out, int64_t n, int64_t per, int accumulate, void* stream);
+
 /* Batched Hungarian matching — scipy.optimize.linear_sum_assignment(cost, maximize) as called by
  * metrics/metric_layoutnet.py:111,125,240 (compute_maximum_iou*, compute_maximum_docsim_for_layout).  fp64 cost
  * [problems, nr, nc] with 1 <= nr, nc <= 16; rows_out / cols_out [problems, min(nr, nc)] in scipy's order; status

@@ -488,3 +488,40 @@ def lsap(cost, maximize=False):
     if single:
         return rows[0], cols[0], status[0]
     return rows, cols, status
+
+
+# ------------------------------------------------------------------------------------------------
+# layout box losses (csrc/box_loss.cu)
+def layout_losses(bbox, valid, want_jac):
+    """bbox [B, N, 4] fp32, valid [B, N] bool/uint8 -> (overlap [B], alignment [B], J_overlap, J_alignment [B, N, 4] or None)."""
+    _cuda(bbox, valid)
+    B, N, _ = bbox.shape
+    bbox = bbox.contiguous()
+    v8 = valid.contiguous().view(torch.uint8) if valid.dtype == torch.bool else valid.to(torch.uint8).contiguous()
+    ov = torch.empty(B, dtype=torch.float32, device=bbox.device)
+    al = torch.empty(B, dtype=torch.float32, device=bbox.device)
+    j_ov = torch.empty_like(bbox) if want_jac else None
+    j_al = torch.empty_like(bbox) if want_jac else None
+    check(lib().ld_layout_losses(_p(bbox), _p(v8), c_int64(B), c_int(N), _p(ov), _p(al), _p(j_ov), _p(j_al), _stream()), "ld_layout_losses")
+    return ov, al, j_ov, j_al
+
+
+def giou_loss(fake, real, want_jac):
+    """fake, real [M, 4] fp32 -> (mean(1 - GIoU) as a 0-dim tensor, d loss / d fake [M, 4] or None)."""
+    _cuda(fake, real)
+    fake, real = fake.contiguous(), real.contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=fake.device)
+    jac = torch.empty_like(fake) if want_jac else None
+    check(lib().ld_giou_loss(_p(fake), _p(real), c_int64(fake.shape[0]), _p(loss), _p(jac), _stream()), "ld_giou_loss")
+    return loss[0], jac
+
+
+def rows_scale(J, g, out=None, accumulate=False):
+    """out (+)= J * g broadcast over J's trailing elements (g: one value per leading row group, or a scalar)."""
+    _cuda(J, g)
+    g = g.reshape(-1).contiguous()
+    per = J.numel() // g.numel()
+    if out is None:
+        out = torch.empty_like(J)
+    check(lib().ld_rows_scale(_p(J), _p(g), _p(out), c_int64(J.numel()), c_int64(per), c_int(1 if accumulate else 0), _stream()), "ld_rows_scale")
+    return out

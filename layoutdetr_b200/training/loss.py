@@ -7,7 +7,7 @@ in the reference's default configuration (`--pl-weight 0 --gamma 0`, train.py) a
 import torch
 import torch.nn.functional as F
 
-from ..metrics.metric_layoutnet import generalized_iou_loss, compute_overlap, compute_alignment
+from ..metrics.metric_layoutnet import generalized_iou_loss, layout_overlap_alignment
 from ..torch_utils import training_stats
 from .. import functional as Fn
 from ..lanes import LANES
@@ -75,13 +75,14 @@ class StyleGAN2Loss(Loss):
             bbox_fake, loss_z, cls_logits, loss_lm, loss_text_len = self.run_G(gen_z, bbox_class, bbox_real, bbox_text, bbox_patch, padding_mask, background, gen_c, reconst=True)
             gen_logits, gen_logits_uncond = self.run_D(bbox_fake, bbox_class, bbox_text, bbox_patch, padding_mask, background, gen_c)
             report('Loss/scores/fake', gen_logits)
+            overlapping, alignment = layout_overlap_alignment(bbox_fake, keep)      # compute_overlap + compute_alignment, one launch
             terms = dict(
                 loss_Ggen=F.softplus(-gen_logits),
                 loss_Ggen_uncond=F.softplus(-gen_logits_uncond),
                 loss_Ggen_bbox_rec=F.mse_loss(sel(bbox_fake), sel(bbox_real)) * W['Ggen_bbox_rec'],
                 loss_Ggen_bbox_gIoU=generalized_iou_loss(sel(bbox_fake), sel(bbox_real)) * W['Ggen_bbox_gIoU'],
-                loss_Ggen_overlapping=compute_overlap(bbox_fake, keep) * W['Ggen_overlapping'],
-                loss_Ggen_alignment=compute_alignment(bbox_fake, keep) * W['Ggen_alignment'],
+                loss_Ggen_overlapping=overlapping * W['Ggen_overlapping'],
+                loss_Ggen_alignment=alignment * W['Ggen_alignment'],
                 loss_Ggen_z_rec=loss_z * W['Ggen_z_rec'],
                 loss_Ggen_bbox_cls=Fn.cross_entropy(cls_logits, sel(bbox_class)) * W['Ggen_bbox_cls'],
                 loss_Ggen_text_rec=loss_lm * W['Ggen_text_rec'],

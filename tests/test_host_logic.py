@@ -28,23 +28,58 @@ def test_make_inputs_contract():
     assert float(a["bbox_real"][:, 8:].abs().max()) == 0.0
 
 
-def test_box_losses_match_oracle_and_have_finite_grads():
-    from layoutdetr_b200 import box_ops
+def _host_box_lib(tmp_path_factory=None):
+    """g++ build of the product's box-loss arithmetic (csrc/box_loss_math.h, shared with the CUDA kernels)."""
+    import ctypes, subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(tempfile.mkdtemp(prefix="ld_boxloss_"), "box_loss_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", out, os.path.join(root, "tests", "native", "box_loss_host.cpp")], check=True)
+    return ctypes.CDLL(out)
+
+
+def test_box_loss_arithmetic_matches_oracle_values_and_autograd():
+    """The arithmetic the box-loss kernels compile (value + analytic Jacobian) against autograd of the oracle restatement of
+    metrics/metric_layoutnet.py:153-201,245-275 — ragged layouts, a single valid slot, junk in padded slots."""
+    import ctypes
     from oracle import layoutdetr_oracle as O
+    lib = _host_box_lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
     g = torch.Generator().manual_seed(0)
-    bbox = torch.rand((4, 9, 4), generator=g) * 0.5 + 0.2
-    mask = torch.ones((4, 9), dtype=torch.bool)
-    mask[:, 7:] = False
-    mask[1, 3:] = False
-    b1 = bbox.clone().requires_grad_(True)
-    b2 = bbox.clone().requires_grad_(True)
-    ours = box_ops.overlap(b1, mask).sum() + box_ops.alignment(b1, mask).sum() + box_ops.giou_loss(b1[mask], bbox.flip(0)[mask])
-    ref = O.compute_overlap(b2, mask).sum() + O.compute_alignment(b2, mask).sum() + O.generalized_iou_loss(b2[mask], bbox.flip(0)[mask])
-    torch.testing.assert_close(ours, ref, atol=1e-5, rtol=1e-5)
-    ours.backward()
-    ref.backward()
-    assert torch.isfinite(b1.grad).all()
-    torch.testing.assert_close(b1.grad, b2.grad, atol=1e-4, rtol=1e-4)
+    for trial in range(8):
+        B, N = 5, 9
+        bbox = torch.rand((B, N, 4), generator=g) * torch.tensor([0.6, 0.6, 0.5, 0.3]) + torch.tensor([0.2, 0.2, 0.05, 0.03])
+        mask = torch.ones((B, N), dtype=torch.bool)
+        mask[:, 8:] = False
+        mask[1, 3:] = False
+        mask[2, 1:] = False
+        if trial % 2 == 0:
+            bbox[:, 8:] = torch.rand((B, 1, 4), generator=g)          # the generator's output in padded slots is arbitrary
+        b2 = bbox.clone().requires_grad_(True)
+        ov, al = O.compute_overlap(b2, mask), O.compute_alignment(b2, mask)
+        w1, w2 = torch.rand(B, generator=g), torch.rand(B, generator=g)
+        ((ov * w1).sum() + (al * w2).sum()).backward()
+        v8 = mask.to(torch.uint8).contiguous()
+        o, a, jo, ja = torch.empty(B), torch.empty(B), torch.empty(B, N, 4), torch.empty(B, N, 4)
+        lib.host_layout_losses(P(bbox), P(v8), ctypes.c_long(B), N, P(o), P(a), P(jo), P(ja))
+        torch.testing.assert_close(o, ov.detach(), atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(a, al.detach(), atol=1e-6, rtol=1e-5)
+        grad = jo * w1[:, None, None] + ja * w2[:, None, None]
+        assert torch.isfinite(grad).all()
+        torch.testing.assert_close(grad, b2.grad, atol=2e-5, rtol=1e-4)
+        f, r = bbox[mask].contiguous(), bbox.flip(0)[mask].contiguous()
+        f2 = f.clone().requires_grad_(True)
+        ref = O.generalized_iou_loss(f2, r)
+        ref.backward()
+        lo, jf = torch.empty(1), torch.empty(f.shape[0], 4)
+        lib.host_giou_loss(P(f), P(r), ctypes.c_long(f.shape[0]), P(lo), P(jf))
+        torch.testing.assert_close(lo[0], ref.detach(), atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(jf, f2.grad, atol=1e-6, rtol=1e-4)
+
+
+def test_box_ops_refuse_cpu_tensors():
+    from layoutdetr_b200 import box_ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        box_ops.layout_losses(torch.rand(2, 9, 4), torch.ones(2, 9, dtype=torch.bool))
 
 
 def _dp_worker(rank, world, port, out):

@@ -195,3 +195,35 @@ def test_layernorm_residual_forward(C, with_res):
     torch.testing.assert_close(y.float(), ref.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(mean, pre.mean(1), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(rstd, (pre.var(1, unbiased=False) + 1e-12).rsqrt(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("V,in_place", [(30524, False), (30524, True), (32000, False), (1028, True)])
+def test_cross_entropy_register_row_path(V, in_place):
+    """bf16 rows with a pitch of pad8(V) (the LM-head logits buffer) take the 128-bit register-row kernel; checked like the
+    generic kernel against fp32 torch, separately and in place (d logits overwrites the logits), pad columns end up zero."""
+    from layoutdetr_b200 import kernels as k
+    g = _gen(V + 1)
+    rows, eps = 77, 0.1
+    Vp = (V + 7) // 8 * 8
+    buf = torch.full((rows, Vp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    logits = buf[:, :V]
+    logits.copy_((torch.randn((rows, V), generator=g, device="cuda") * 3).to(torch.bfloat16))
+    labels = torch.randint(0, V, (rows,), generator=g, device="cuda")
+    labels[::5] = -100
+    labels[1] = V - 1
+    labels[2] = 0
+    n_valid = int((labels != -100).sum())
+    lr = logits.float().clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels, label_smoothing=eps, ignore_index=-100)
+    ref.backward()
+    if in_place:
+        dl = logits
+    else:
+        dbuf = torch.full((rows, Vp), float("nan"), dtype=torch.bfloat16, device="cuda")
+        dl = dbuf[:, :V]
+    loss_rows = k.cross_entropy(logits, labels, eps, -100, True, dl, grad_scale=1.0 / n_valid)
+    torch.testing.assert_close(loss_rows.sum() / n_valid, ref, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(dl.float(), lr.grad, atol=2e-5, rtol=2e-2)
+    if Vp > V:
+        pad = (buf if in_place else dbuf)[:, V:]
+        assert float(pad.float().abs().max()) == 0.0
