@@ -238,6 +238,12 @@ int ld_layout_losses(const float* bbox, const uint8_t* valid, int64_t B, int N, 
                      float* j_overlap, float* j_alignment, void* stream);
 int ld_giou_loss(const float* fake, const float* real, int64_t M, float* loss, float* j_fake, void* stream);
 int ld_rows_scale(const float* J, const float* g, float* out, int64_t n, int64_t per, int accumulate, void* stream);
+/* Evaluation sweep (metrics/overlap50k_alignment50k_layoutwise_iou50k_layoutwise_docsim50k.py:36-45, replacing the per-layout
+ * NumPy loop over metrics/metric_layoutnet.py compute_iou_for_layout :94-97 and compute_docsim_for_layout :224-226):
+ * real, fake [B, N, 4] fp32, valid [B, N] bytes -> iou[b], docsim[b] = mean over the valid slots of IoU(real_i, fake_i)
+ * (NaN -> 0) and of sqrt(min(area)) * 2^(-|d centre| - 2 |d shape|). */
+int ld_layout_pair_metrics(const float* real, const float* fake, const uint8_t* valid, int64_t B, int N, float* iou,
+                           float* docsim, void* stream);
 
 /* Batched Hungarian matching — scipy.optimize.linear_sum_assignment(cost, maximize) as called by
  * metrics/metric_layoutnet.py:111,125,240 (compute_maximum_iou*, compute_maximum_docsim_for_layout).  fp64 cost

@@ -45,6 +45,27 @@ layout_losses_kernel(const float* __restrict__ bbox, const uint8_t* __restrict__
     }
 }
 
+// evaluation sweep: per layout, mean over the valid slots of IoU(real_i, fake_i) and of the DocSim weight
+// (metrics/overlap50k_alignment50k_layoutwise_iou50k_layoutwise_docsim50k.py:36-45).  One warp per layout.
+__global__ void __launch_bounds__(128)
+layout_pair_metrics_kernel(const float* __restrict__ real, const float* __restrict__ fake, const uint8_t* __restrict__ valid,
+                           long B, int N, float* __restrict__ iou, float* __restrict__ docsim) {
+    const long b = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float si = 0.f, sd = 0.f, n = 0.f;
+    for (int i = lane; i < N; i += 32) {
+        if (!valid[b * N + i]) continue;
+        const float4 p = reinterpret_cast<const float4*>(real)[b * N + i], q = reinterpret_cast<const float4*>(fake)[b * N + i];
+        const float pf[4] = {p.x, p.y, p.z, p.w}, qf[4] = {q.x, q.y, q.z, q.w};
+        si += ldbox::iou_pair(pf, qf);
+        sd += ldbox::docsim_pair(pf, qf);
+        n += 1.f;
+    }
+    si = ld::warp_sum(si); sd = ld::warp_sum(sd); n = ld::warp_sum(n);
+    if (lane == 0) { iou[b] = si / n; docsim[b] = sd / n; }
+}
+
 constexpr int GIOU_THREADS = 256;
 // one CTA: mean over M index-paired rows of 1 - GIoU; J[m, :] = d mean / d fake[m, :]
 __global__ void __launch_bounds__(GIOU_THREADS)
@@ -112,5 +133,18 @@ extern "C" int ld_rows_scale(const float* J, const float* g, float* out, int64_t
     rows_scale_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(J, g, out, (long)n, (long)per, accumulate);
     ld::count_launch();
     LD_LAUNCH_CHECK("ld_rows_scale");
+    return 0;
+}
+
+extern "C" int ld_layout_pair_metrics(const float* real, const float* fake, const uint8_t* valid, int64_t B, int N, float* iou,
+                                      float* docsim, void* stream) {
+    LD_CHECK_ARG(real && fake && valid && iou && docsim, "ld_layout_pair_metrics: null pointer");
+    LD_CHECK_ARG(N >= 1, "ld_layout_pair_metrics: N = %d", N);
+    LD_CHECK_ARG(((reinterpret_cast<uintptr_t>(real) | reinterpret_cast<uintptr_t>(fake)) & 15) == 0,
+                 "ld_layout_pair_metrics: box buffers must be 16-byte aligned");
+    if (B <= 0) return 0;
+    layout_pair_metrics_kernel<<<(unsigned)((B + 3) / 4), 128, 0, (cudaStream_t)stream>>>(real, fake, valid, (long)B, N, iou, docsim);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("ld_layout_pair_metrics");
     return 0;
 }

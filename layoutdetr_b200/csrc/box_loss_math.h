@@ -199,4 +199,26 @@ LD_HD float alignment_box(const float* bbox, const uint8_t* valid, int N, int i,
     return term;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// evaluation metrics of one index-paired box pair (metrics/metric_layoutnet.py compute_iou :65-91,
+// compute_docsim_weight :204-221); no gradients
+// ---------------------------------------------------------------------------------------------------------------
+LD_HD float iou_pair(const float* p4, const float* q4) {
+    const Ltrb p = to_ltrb(p4), q = to_ltrb(q4);
+    const float a1 = (p.r - p.l) * (p.b - p.t), a2 = (q.r - q.l) * (q.b - q.t);
+    const float lmax = fmaxf(p.l, q.l), rmin = fminf(p.r, q.r), tmax = fmaxf(p.t, q.t), bmin = fminf(p.b, q.b);
+    const bool cond = (lmax < rmin) && (tmax < bmin);
+    const float ai = cond ? (rmin - lmax) * (bmin - tmax) : 0.f;
+    bool pass;
+    return nan_to_num_f(ai / (a1 + a2 - ai), &pass);
+}
+
+LD_HD float docsim_pair(const float* p, const float* q) {
+    const float dx = p[0] - q[0], dy = p[1] - q[1];
+    const float location_difference = sqrtf(dx * dx + dy * dy);
+    const float shape_difference = fabsf(p[2] - q[2]) + fabsf(p[3] - q[3]);
+    const float area_factor = sqrtf(fminf(p[2] * p[3], q[2] * q[3]));
+    return area_factor * exp2f(-location_difference - 2.0f * shape_difference);
+}
+
 }  // namespace ldbox

@@ -525,3 +525,15 @@ def rows_scale(J, g, out=None, accumulate=False):
         out = torch.empty_like(J)
     check(lib().ld_rows_scale(_p(J), _p(g), _p(out), c_int64(J.numel()), c_int64(per), c_int(1 if accumulate else 0), _stream()), "ld_rows_scale")
     return out
+
+
+def layout_pair_metrics(real, fake, valid):
+    """real, fake [B, N, 4] fp32, valid [B, N] -> (layout-wise IoU [B], layout-wise DocSim [B])."""
+    _cuda(real, fake, valid)
+    B, N, _ = real.shape
+    real, fake = real.float().contiguous(), fake.float().contiguous()
+    v8 = valid.contiguous().view(torch.uint8) if valid.dtype == torch.bool else valid.to(torch.uint8).contiguous()
+    iou = torch.empty(B, dtype=torch.float32, device=real.device)
+    doc = torch.empty(B, dtype=torch.float32, device=real.device)
+    check(lib().ld_layout_pair_metrics(_p(real), _p(fake), _p(v8), c_int64(B), c_int(N), _p(iou), _p(doc), _stream()), "ld_layout_pair_metrics")
+    return iou, doc

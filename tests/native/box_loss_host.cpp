@@ -35,3 +35,18 @@ extern "C" void host_giou_loss(const float* fake, const float* real, long M, flo
     }
     loss[0] = (float)(acc * inv);
 }
+
+extern "C" void host_layout_pair_metrics(const float* real, const float* fake, const uint8_t* valid, long B, int N, float* iou,
+                                         float* docsim) {
+    for (long b = 0; b < B; ++b) {
+        float si = 0.f, sd = 0.f, n = 0.f;
+        for (int i = 0; i < N; ++i) {
+            if (!valid[b * N + i]) continue;
+            si += ldbox::iou_pair(real + (b * N + i) * 4, fake + (b * N + i) * 4);
+            sd += ldbox::docsim_pair(real + (b * N + i) * 4, fake + (b * N + i) * 4);
+            n += 1.f;
+        }
+        iou[b] = si / n;
+        docsim[b] = sd / n;
+    }
+}

@@ -99,6 +99,53 @@ def gen_hungarian():
     print("hungarian goldens:", len(cases))
 
 
+def gen_eval():
+    """Evaluation-sweep pieces of the reference: LayoutNet.extract_features (FID features, synthetic weights), per-layout
+    IoU / DocSim, overlap / alignment, FeatureStats moments + the layout-FID formula."""
+    import numpy as np
+    import scipy.linalg
+    from training.networks_layoutnet import LayoutNet
+    from metrics import metric_layoutnet as ml
+    from metrics.metric_utils_layout import FeatureStats
+    net = LayoutNet(13).eval()
+    synth_state_dict(net)
+    g = torch.Generator().manual_seed(11)
+    B, N = 640, 9                                            # > 256 layouts so that the feature covariances have full rank
+    scale, shift = torch.tensor([0.6, 0.6, 0.5, 0.3]), torch.tensor([0.2, 0.2, 0.05, 0.03])
+    bbox_real = torch.rand((B, N, 4), generator=g) * scale + shift
+    bbox_fake = (bbox_real + 0.08 * torch.randn((B, N, 4), generator=g)).clamp(0.01, 0.99)
+    label = torch.randint(0, 13, (B, N), generator=g)
+    n_valid = torch.randint(1, N + 1, (B,), generator=g)
+    mask = torch.arange(N)[None, :] < n_valid[:, None]
+    bbox_real = bbox_real * mask[..., None]
+    with torch.no_grad():
+        f_real = net.extract_features(bbox_real, label.clone(), ~mask)
+        f_fake = net.extract_features(bbox_fake, label.clone(), ~mask)
+        overlap = ml.compute_overlap(bbox_fake, mask)
+        alignment = ml.compute_alignment(bbox_fake, mask)
+    iou, docsim = [], []
+    for j in range(B):
+        m = mask[j].numpy()
+        br, bf, l = bbox_real[j].numpy()[m], bbox_fake[j].numpy()[m], label[j].numpy()[m]
+        iou.append(ml.compute_iou_for_layout((br, l), (bf, l)))
+        docsim.append(ml.compute_docsim_for_layout((br, l), (bf, l)))
+    st_r, st_f = FeatureStats(capture_mean_cov=True), FeatureStats(capture_mean_cov=True)
+    st_r.append_torch(f_real)
+    st_f.append_torch(f_fake)
+    mu_r, s_r = st_r.get_mean_cov()
+    mu_f, s_f = st_f.get_mean_cov()
+    m = np.square(mu_f - mu_r).sum()                          # metrics/layout_frechet_inception_distance.py:36-39
+    s = scipy.linalg.sqrtm(np.dot(s_f, s_r))                  # scipy >= 1.16 dropped `disp`; 1.6.3 returned (sqrtm, errest) with disp=False
+    fid = float(np.real(m + np.trace(s_f + s_r - s * 2)))
+    out = dict(bbox_real=bbox_real, bbox_fake=bbox_fake, label=label, mask=mask, f_real=f_real[:32].clone(), f_fake=f_fake[:32].clone(),
+               overlap=overlap, alignment=alignment, iou=torch.tensor(iou, dtype=torch.float64),
+               docsim=torch.tensor(docsim, dtype=torch.float64), fid=fid,
+               layoutnet_keys={k: list(v.shape) for k, v in net.state_dict().items()})
+    torch.save(out, os.path.join(GOLD, "eval_ref.pt"))
+    print("eval goldens: fid %.6f, mean overlap %.5f alignment %.5f iou %.5f docsim %.5f" % (
+        fid, float(overlap.mean()), float(alignment.mean()), float(np.mean(iou)), float(np.mean(docsim))))
+
+
 def run_model_goldens(nd, G, D, name, batch, n_valid, seed):
     inp = make_inputs(batch, n_valid=n_valid, seed=seed)
     store = {}
@@ -177,12 +224,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-loss", action="store_true")
     ap.add_argument("--skip-model", action="store_true")
+    ap.add_argument("--only-eval", action="store_true", help="regenerate tests/golden/eval_ref.pt only")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     nd = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
+    if args.only_eval:
+        gen_eval()
+        return
     gen_ops()
     gen_hungarian()
+    gen_eval()
     if args.skip_model:
         return
     torch.manual_seed(0)

@@ -40,7 +40,7 @@ bn3_s = torch.rand(256, device=dev) + 0.5; bn3_b = torch.randn(256, device=dev)
 # LM-head CE rows: 16 sequences x 256 tokens over the 30524-way vocabulary (padded row pitch 30528)
 logits = torch.randn((16 * 256, 30528), device=dev).to(torch.bfloat16)[:, :30524]
 labels = torch.randint(0, 30524, (16 * 256,), device=dev)
-dlog = torch.empty_like(logits)
+dlog = logits                                                     # in place, as LMHeadCEFn does
 # flat Adam over 16 M parameters
 n = 16 * 1024 * 1024
 p = torch.randn(n, device=dev); gr = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
