@@ -663,9 +663,11 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
 
     const int sms = sm_count();
     const int cta_limit = cta_limit_for(stream);       // persistent grid cap of this stream's lane (default: every SM)
-    // CTA pairs (cta_group::2) for problems with enough 256 x 256 tiles to fill the chip: opt-in with LD_GEMM_2SM=1
-    // (measured neutral on B200 for the BERT shapes: the 1-CTA mainloop is clock/power- rather than L2-limited)
-    static const int env_2sm = [] { const char* e = getenv("LD_GEMM_2SM"); return e ? atoi(e) : 0; }();
+    // CTA pairs (cta_group::2) for problems with enough 256 x 256 tiles to fill the chip; LD_GEMM_2SM=0 turns them off.
+    // Each CTA of a pair loads half of the B tile, so the L2 -> shared-memory fill per MMA drops by a quarter: measured on the
+    // full training iteration 96.3 -> 93.5 ms per step, and 1213 -> 1249 TFLOP/s on the 36864 x 3072 x 768 GEMM alone
+    // (profiles/r1_bench_n1_gemm_2sm.json vs r1_bench_n1.json, same box, back to back).
+    static const int env_2sm = [] { const char* e = getenv("LD_GEMM_2SM"); return e ? atoi(e) : 1; }();
     const long nb_ = (long)d->nb1 * d->nb2;
     const bool two_sm = env_2sm && d->block_n != 128 && d->N > 128 && d->M >= 256 && !d->softmax &&
                         nb_ * ceil_div(d->M, 256) * ceil_div(d->N, 256) * d->split_k >= (sms / 2);

@@ -150,3 +150,43 @@ def test_engine_refresh_stale_recomputes_in_place():
     assert E.refresh_stale({id(p)}) == 1
     v2 = E.derived((p,), "twice", lambda: None)       # cache hit, no recompute
     assert v2.data_ptr() == ptr and torch.equal(v2, (p.detach() * 2))
+
+
+def _eval_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from layoutdetr_b200.metrics.eval_sweep import LayoutEvalAccumulator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn((2, 40, 16), generator=g, dtype=torch.float64)       # [real | fake], 40 layouts, split over the ranks
+    vals = torch.rand((4, 40), generator=g, dtype=torch.float64)
+    acc = LayoutEvalAccumulator(feature_dim=16, device="cpu")
+    sl = slice(rank, 40, world)                                               # the reference's interleaved item subset
+    acc.n += vals[:, sl].shape[1]
+    acc.sums += vals[:, sl].sum(dim=1)
+    for i in range(2):
+        acc.raw_mean[i] += feats[i, sl].sum(dim=0)
+        acc.raw_cov[i] += feats[i, sl].t() @ feats[i, sl]
+    res = acc.all_reduce().result()
+    if rank == 0:
+        torch.save(dict(res=res, feats=feats, vals=vals), out)
+    dist.destroy_process_group()
+
+
+def test_eval_sweep_exchange_step_two_ranks_gloo(tmp_path):
+    """The eval sweep's only collective: one SUM all-reduce of the running statistics; 2 ranks == 1 process on all items."""
+    import torch.multiprocessing as mp
+    from oracle import layoutdetr_oracle as O
+    out = str(tmp_path / "eval.pt")
+    mp.spawn(_eval_worker, args=(2, 29517 + os.getpid() % 1000, out), nprocs=2, join=True)
+    d = torch.load(out, weights_only=False)
+    res, feats, vals = d["res"], d["feats"], d["vals"]
+    assert res["num_items"] == 40
+    for k, i in [("overlap", 0), ("alignment", 1), ("layoutwise_iou", 2), ("layoutwise_docsim", 3)]:
+        assert abs(res[k] - float(vals[i].mean())) < 1e-12
+    x = feats.numpy()
+    mean = [x[i].sum(0) / 40 for i in range(2)]
+    cov = [x[i].T @ x[i] / 40 - __import__("numpy").outer(mean[i], mean[i]) for i in range(2)]
+    ref = O.layout_fid(mean[1], cov[1], mean[0], cov[0])
+    assert abs(res["layout_fid"] - ref) <= 1e-9 * max(1.0, abs(ref))

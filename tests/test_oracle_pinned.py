@@ -67,3 +67,58 @@ def test_oracle_discriminator_matches_reference(name):
             assert abs(float(val.mean()) - g["D"]["bg_rec_mean"]) < 1e-3 * max(1.0, abs(g["D"]["bg_rec_std"]))
         else:
             torch.testing.assert_close(val, g["D"][key], atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation sweep: goldens in eval_ref.pt come from the reference's LayoutNet, metric functions,
+# FeatureStats and layout-FID formula (tools/gen_golden.py gen_eval)
+# ------------------------------------------------------------------------------------------------
+def _layoutnet_sd():
+    from layoutdetr_b200.synthetic import synth_state_dict
+    from layoutdetr_b200.training.networks_layoutnet import LayoutNet
+    net = LayoutNet(13)
+    return net, synth_state_dict(net)
+
+
+def test_layoutnet_state_dict_tree_matches_reference():
+    g = golden("eval_ref.pt")
+    net, _ = _layoutnet_sd()
+    assert {k: list(v.shape) for k, v in net.state_dict().items()} == g["layoutnet_keys"]
+
+
+def test_oracle_eval_sweep_matches_reference():
+    from oracle import layoutdetr_oracle as O
+    g = golden("eval_ref.pt")
+    _, sd = _layoutnet_sd()
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+    real, fake, label, mask = g["bbox_real"], g["bbox_fake"], g["label"], g["mask"]
+    with torch.no_grad():
+        f_real = O.layoutnet_extract_features(sd, real, label, ~mask)
+        f_fake = O.layoutnet_extract_features(sd, fake, label, ~mask)
+    torch.testing.assert_close(f_real[:32], g["f_real"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(f_fake[:32], g["f_fake"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(O.compute_overlap(fake, mask), g["overlap"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(O.compute_alignment(fake, mask), g["alignment"], atol=1e-6, rtol=1e-5)
+    iou, doc = O.layoutwise_iou_docsim(real, fake, mask)
+    torch.testing.assert_close(iou.double(), g["iou"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(doc.double(), g["docsim"], atol=1e-6, rtol=1e-5)
+    mu_r, s_r = O.feature_mean_cov(f_real.numpy())
+    mu_f, s_f = O.feature_mean_cov(f_fake.numpy())
+    fid = O.layout_fid(mu_f, s_f, mu_r, s_r)
+    assert abs(fid - g["fid"]) <= 1e-4 * abs(g["fid"]) + 1e-7, (fid, g["fid"])
+
+
+def test_pair_metric_arithmetic_matches_reference_goldens():
+    """The arithmetic ld_layout_pair_metrics compiles (host build of csrc/box_loss_math.h) on the reference's own outputs."""
+    import ctypes
+    from test_host_logic import _host_box_lib
+    g = golden("eval_ref.pt")
+    lib = _host_box_lib()
+    real, fake = g["bbox_real"].contiguous(), g["bbox_fake"].contiguous()
+    v8 = g["mask"].to(torch.uint8).contiguous()
+    B, N = v8.shape
+    iou, doc = torch.empty(B), torch.empty(B)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib.host_layout_pair_metrics(P(real), P(fake), P(v8), ctypes.c_long(B), N, P(iou), P(doc))
+    torch.testing.assert_close(iou.double(), g["iou"], atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(doc.double(), g["docsim"], atol=1e-6, rtol=1e-5)
