@@ -245,6 +245,12 @@ int ld_rows_scale(const float* J, const float* g, float* out, int64_t n, int64_t
 int ld_layout_pair_metrics(const float* real, const float* fake, const uint8_t* valid, int64_t B, int N, float* iou,
                            float* docsim, void* stream);
 
+/* Data-loader tail (training/dataset_layoutganpp.py:333-336): uint8 HWC images [B, H, W, 3] -> fp32 NCHW [B, 3, H, W],
+ * (x / 255 - mean[c]) / std[c] with IEEE fp32 division in the reference's order (bit-identical to its NumPy expression).
+ * mean3 / std3 are HOST pointers to 3 floats; H*W % 4 == 0. */
+int ld_normalize_u8_image(const uint8_t* src_hwc, float* dst_nchw, int64_t B, int64_t H, int64_t W, const float* mean3,
+                          const float* std3, void* stream);
+
 /* Batched Hungarian matching — scipy.optimize.linear_sum_assignment(cost, maximize) as called by
  * metrics/metric_layoutnet.py:111,125,240 (compute_maximum_iou*, compute_maximum_docsim_for_layout).  fp64 cost
  * [problems, nr, nc] with 1 <= nr, nc <= 16; rows_out / cols_out [problems, min(nr, nc)] in scipy's order; status

@@ -794,3 +794,50 @@ int ld_channel_dot(const void* a, int a_dtype, const void* g_bf16, float* out, i
     return 0;
 }
 }  // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Data-loader tail: uint8 HWC image batch -> fp32 NCHW normalised with per-channel mean / std, the arithmetic of the
+// reference loader (training/dataset_layoutganpp.py:333-336: x.astype(float32) / 255.0 - mean) / std) in the same order
+// with IEEE fp32 division, so the result is bit-identical to NumPy's while the host ships 1 byte per value instead of 4.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+normalize_u8_hwc_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long pixels_per_image, long total_pixels,
+                        float m0, float m1, float m2, float s0, float s1, float s2) {
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g * 4 < total_pixels; g += (long)gridDim.x * blockDim.x) {
+        const long p0 = g * 4;                                    // four consecutive pixels of one image (pixels_per_image % 4 == 0)
+        const long b = p0 / pixels_per_image, q = p0 - b * pixels_per_image;
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + p0 * 3);          // 12 bytes = 3 aligned words
+        const uint32_t w0 = __ldg(s32), w1 = __ldg(s32 + 1), w2 = __ldg(s32 + 2);
+        const uint8_t v[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
+                               (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
+                               (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v[3 * k + c], 255.0f), mean[c]), stdv[c]);
+            *reinterpret_cast<float4*>(dst + (b * 3 + c) * pixels_per_image + q) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int ld_normalize_u8_image(const uint8_t* src_hwc, float* dst_nchw, int64_t B, int64_t H, int64_t W, const float* mean3,
+                                     const float* std3, void* stream) {
+    LD_CHECK_ARG(src_hwc && dst_nchw && mean3 && std3 && B > 0 && H > 0 && W > 0, "normalize_u8_image: bad argument");
+    const long ppi = (long)H * W;
+    LD_CHECK_ARG(ppi % 4 == 0, "normalize_u8_image: H*W = %ld must be a multiple of 4", ppi);
+    LD_CHECK_ARG((reinterpret_cast<uintptr_t>(src_hwc) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_nchw) & 15) == 0,
+                 "normalize_u8_image: buffers must be 4- / 16-byte aligned");
+    const long groups = (long)B * ppi / 4;
+    const int grid = (int)std::min<long>((groups + 255) / 256, (long)ld::sm_count() * 8);
+    normalize_u8_hwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_hwc, dst_nchw, ppi, (long)B * ppi, mean3[0], mean3[1], mean3[2],
+                                                                    std3[0], std3[1], std3[2]);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("normalize_u8_image");
+    return 0;
+}

@@ -537,3 +537,16 @@ def layout_pair_metrics(real, fake, valid):
     doc = torch.empty(B, dtype=torch.float32, device=real.device)
     check(lib().ld_layout_pair_metrics(_p(real), _p(fake), _p(v8), c_int64(B), c_int(N), _p(iou), _p(doc), _stream()), "ld_layout_pair_metrics")
     return iou, doc
+
+
+def normalize_u8_image(img_u8, mean, std):
+    """uint8 [B, H, W, 3] (CUDA) -> fp32 [B, 3, H, W] = (x / 255 - mean) / std, bit-identical to the reference loader's NumPy."""
+    _cuda(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.ndim == 4 and img_u8.shape[-1] == 3
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    m = (c_float * 3)(*[float(x) for x in mean])
+    s = (c_float * 3)(*[float(x) for x in std])
+    check(lib().ld_normalize_u8_image(_p(img_u8), _p(out), c_int64(B), c_int64(H), c_int64(W), m, s, _stream()), "ld_normalize_u8_image")
+    return out

@@ -21,6 +21,8 @@ import training.networks_detr as nd, torch_utils.ops.bias_act as ba, torch_utils
 import torch_utils.ops.conv2d_gradfix as cg, torch_utils.misc as misc, dnnlib
 assert nd.Generator.__module__ == "layoutdetr_b200.training.networks_detr", nd.Generator.__module__
 assert "layoutdetr_b200" in ba.bias_act.__module__ and "layoutdetr_b200" in uf.upfirdn2d.__module__
+import training.networks_layoutnet as ln, training.dataset_layoutganpp as dsl
+assert ln.LayoutNet.__module__ == "layoutdetr_b200.training.networks_layoutnet" and "layoutdetr_b200" in dsl.LayoutDataset.__module__
 assert hasattr(cg, "no_weight_gradients") and misc.__file__.startswith(%r) and dnnlib.__file__.startswith(%r)
 print("OVERLAY_OK")
 ''' % (REF, REF)

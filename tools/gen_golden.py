@@ -146,6 +146,65 @@ def gen_eval():
         fid, float(overlap.mean()), float(alignment.mean()), float(np.mean(iou)), float(np.mean(docsim))))
 
 
+def make_tiny_layout_zip(path, seed=3):
+    """A tiny dataset in the reference's on-disk format (dataset_tool.py output: non_image.json + per-sample PNGs)."""
+    import io, json, zipfile
+    import numpy as np
+    import PIL.Image
+    rng = np.random.RandomState(seed)
+    H, W = 48, 64                                              # page size (real data: 1024-class pages)
+
+    def smooth(h, w, c=3):
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.stack([127 + 120 * np.sin(xx / (3 + 5 * rng.rand()) + 6 * rng.rand()) * np.cos(yy / (2 + 6 * rng.rand())) for _ in range(c)], -1)
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    samples = []
+    with zipfile.ZipFile(path, "w", zipfile.ZIP_STORED) as z:
+        def put(name, arr):
+            buf = io.BytesIO()
+            PIL.Image.fromarray(arr).save(buf, format="PNG")
+            z.writestr(name, buf.getvalue())
+        for si, n in enumerate([3, 9, 1]):
+            base = "page_%02d" % si
+            bboxes = np.round(np.stack([rng.uniform(0.2, 0.8, n), rng.uniform(0.2, 0.8, n), rng.uniform(0.1, 0.6, n), rng.uniform(0.03, 0.2, n)], -1), 4)
+            for i in range(n):
+                ph, pw = [(10, 30), (26, 12), (16, 16)][i % 3]
+                put("%s_%d_patch.png" % (base, i), smooth(ph, pw))
+                put("%s_%d_patch_orig.png" % (base, i), smooth(H, W))
+                put("%s_%d_patch_mask.png" % (base, i), (smooth(H, W, 1)[:, :, 0] > 127).astype(np.uint8) * 255)
+            put(base + "_background_orig.png", smooth(H, W))
+            samples.append([base, dict(bboxes=bboxes.tolist(), labels=[int(v) for v in rng.randint(0, 8, n)],
+                                       texts=["text %d of page %d" % (i, si) for i in range(n)], page_label=None,
+                                       attr=dict(name=base, width=W, height=H, num_bbox_labels=8))])
+        z.writestr("non_image.json", json.dumps(dict(samples=samples)))
+
+
+def gen_dataset():
+    """tests/golden/tiny_layout.zip + what the reference's LayoutDataset returns for it (background_size 32)."""
+    import numpy as np
+    import PIL.Image
+    np.bool = bool                                             # NumPy 2 / Pillow 12 drift (training/dataset_layoutganpp.py:37,296)
+    PIL.Image.ANTIALIAS = PIL.Image.LANCZOS
+    from training.dataset_layoutganpp import LayoutDataset
+    path = os.path.join(GOLD, "tiny_layout.zip")
+    make_tiny_layout_zip(path)
+    ds = LayoutDataset(path=path, use_labels=False, max_size=None, xflip=False, background_size=32)
+    out = dict(len=len(ds), patch_shape=ds.patch_shape, num_bbox_labels=ds.num_bbox_labels, label_dim=ds.label_dim, name=ds.name, items=[])
+    for i in range(len(ds)):
+        s, lab = ds[i]
+        out["items"].append(dict(
+            bboxes=torch.from_numpy(s["bboxes"]), labels=torch.from_numpy(s["labels"]), texts=s["texts"], mask=torch.from_numpy(s["mask"]),
+            background=torch.from_numpy(s["background"]), name=s["name"], W_page=s["W_page"], H_page=s["H_page"], label=torch.from_numpy(lab),
+            patches_sum=float(s["patches"].astype(np.float64).sum()), patches_abs=float(np.abs(s["patches"]).astype(np.float64).sum()),
+            patches_sub=torch.from_numpy(s["patches"][:, :, ::16, ::16].copy()),
+            patches_orig_sum=float(s["patches_orig"].astype(np.float64).sum()), patches_orig_shape=list(s["patches_orig"].shape),
+            patch_masks_sum=float(s["patch_masks"].astype(np.float64).sum()), patch_masks_shape=list(s["patch_masks"].shape),
+            background_orig_sum=float(s["background_orig"].astype(np.float64).sum())))
+    torch.save(out, os.path.join(GOLD, "dataset_ref.pt"))
+    print("dataset goldens:", out["len"], "samples, patch_shape", out["patch_shape"])
+
+
 def run_model_goldens(nd, G, D, name, batch, n_valid, seed):
     inp = make_inputs(batch, n_valid=n_valid, seed=seed)
     store = {}
@@ -225,6 +284,7 @@ def main():
     ap.add_argument("--skip-loss", action="store_true")
     ap.add_argument("--skip-model", action="store_true")
     ap.add_argument("--only-eval", action="store_true", help="regenerate tests/golden/eval_ref.pt only")
+    ap.add_argument("--only-dataset", action="store_true", help="regenerate tests/golden/tiny_layout.zip + dataset_ref.pt only")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     nd = ref_shim.load()
@@ -232,9 +292,13 @@ def main():
     if args.only_eval:
         gen_eval()
         return
+    if args.only_dataset:
+        gen_dataset()
+        return
     gen_ops()
     gen_hungarian()
     gen_eval()
+    gen_dataset()
     if args.skip_model:
         return
     torch.manual_seed(0)
