@@ -121,6 +121,78 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+def run_eval(args):
+    """`--workload eval` (BASELINE configs[4]): the evaluation sweep — G_ema forward at 64 layouts per
+    batch, LayoutNet features of real and generated layouts, overlap / alignment / layout-wise IoU / DocSim, FID — through
+    layoutdetr_b200.metrics.eval_sweep.run_sweep with host batches (H2D inside the timed region, D2H of the metric dict),
+    next to the CPU oracle of the same sweep on a bounded sample.  Single GPU; one JSON line."""
+    import torch
+    from layoutdetr_b200 import _lib
+    from layoutdetr_b200.synthetic import SyntheticTokenizer, make_inputs
+    from layoutdetr_b200.training import networks_detr as nd
+    from layoutdetr_b200.training.networks_layoutnet import LayoutNet
+    from layoutdetr_b200.metrics import eval_sweep
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _lib.lib()
+    torch.manual_seed(0)
+    G = nd.Generator(**G_KWARGS).to(dev).eval().requires_grad_(False)
+    net = LayoutNet(13).to(dev).eval().requires_grad_(False)
+    B, nb = args.eval_batch, max(1, args.steps)
+    host = [make_inputs(B, n_valid=8, seed=50 + i) for i in range(nb)]
+    for hb in host:
+        for k, v in hb.items():
+            if torch.is_tensor(v):
+                hb[k] = v.pin_memory()
+    to_dev = lambda hb: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+    for _ in range(max(1, args.warmup)):
+        eval_sweep.run_sweep(G, net, [to_dev(host[0])])                  # tokeniser cache, weight shadows
+    torch.cuda.synchronize()
+    _lib.launch_count_reset()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    t0 = time.perf_counter()
+    res = eval_sweep.run_sweep(G, net, (to_dev(hb) for hb in host))     # one sweep over `steps` batches
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n = B * nb
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import layoutdetr_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sdG = {k: v.detach().cpu() for k, v in G.state_dict().items()}
+        sdL = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        inp = make_inputs(args.cpu_sample, n_valid=8, seed=50)
+        tok = SyntheticTokenizer()
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            fake = O.generator_forward(sdG, tok, inp["z"], inp["bbox_class"], inp["bbox_text"], inp["padding_mask"], inp["background"])
+            mask = ~inp["padding_mask"]
+            O.layoutnet_extract_features(sdL, inp["bbox_real"], inp["bbox_class"], inp["padding_mask"])
+            O.layoutnet_extract_features(sdL, fake, inp["bbox_class"], inp["padding_mask"])
+            O.compute_overlap(fake, mask), O.compute_alignment(fake, mask), O.layoutwise_iou_docsim(inp["bbox_real"], fake, mask)
+        cpu_sec = time.perf_counter() - t1
+        cpu = dict(value=args.cpu_sample / cpu_sec, unit="layouts/s", cores=threads, kind="port",
+                   sample="%d layouts, oracle sweep (%.1f s)" % (args.cpu_sample, cpu_sec))
+    gf = 425.2                                                           # SURVEY §8d: G.forward(reconst=False) GFLOP per sample
+    line = dict(metric="eval-sweep layouts/sec (G_ema fwd + LayoutNet features + overlap/alignment/IoU/DocSim + layout FID)",
+                value=n / sec, unit="layouts/s", n_gpus=1, steps=nb, warmup=args.warmup, ms_per_step=sec / nb * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload="eval sweep, %d layouts per batch, 256x256 backgrounds, 8 of 9 slots (BASELINE configs[4] shapes)" % B,
+                            batch_per_gpu=B, l2="inputs larger than L2 per batch (text activations 680 MB)", timing="host clock around the public API call"),
+                clocks=clocks, e2e=dict(value=n / sec, unit="layouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=8 * 6),
+                gpu_launches=int(_lib.launch_count()),
+                roofline=dict(bound="tensor", achieved=n / sec * gf / 1e3, peak=peaks()["sustained"], unit="TFLOP/s",
+                              frac=n / sec * gf / 1e3 / peaks()["sustained"], traffic=None, gflop_per_layout=gf,
+                              note="whole sweep against the algorithmic forward FLOPs (dense reference shapes)"),
+                cpu_baseline=cpu, result=res)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------
 def gemm_roofline(torch, K, pk):
     """Dominant kernel (gemm_bf16_kernel) on the dominant shape — the BERT FFN GEMM of one text-encoder call at bs16:
     M = 16*9*256 tokens, N = 3072, K = 768 — timed alone with CUDA events on the launching stream."""
@@ -146,8 +218,11 @@ def gemm_roofline(torch, K, pk):
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from the ncu --set full capture in
     # profiles/r1_gemm_ncu_full_epilogue_variants.txt (61.5 MB read + 174.3 MB written; algorithmic: 61.3 + 226.5 MB, part of the
     # output still sits in L2 when the kernel ends)
+    two_sm = os.environ.get("LD_GEMM_2SM", "1") != "0"      # this shape has 1728 pair tiles: the cta_group::2 kernel unless disabled
     return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=235.7e6,
-                kernel="gemm_bf16_kernel", shape=[M, N, Kd], ms=ms, peak_source=pk["src"] + " burst (kernel timed alone)")
+                traffic_note="ncu --set full capture of the single-CTA kernel on this shape (profiles/r1_gemm_ncu_full_epilogue_variants.txt)",
+                kernel="gemm_bf16_2sm_kernel (cta_group::2)" if two_sm else "gemm_bf16_kernel", shape=[M, N, Kd], ms=ms,
+                peak_source=pk["src"] + " burst (kernel timed alone)")
 
 
 def run_ours(args):
@@ -336,6 +411,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch samples on every GPU (default); strong: --batch samples split over the GPUs (reference --batch=16 semantics)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="samples in the bounded CPU-baseline step")
+    ap.add_argument("--workload", default="train", choices=["train", "eval"],
+                    help="train: the headline training iteration (default); eval: the evaluation sweep at --eval-batch layouts per batch")
+    ap.add_argument("--eval-batch", type=int, default=64)
     ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
     ap.add_argument("--graph", type=int, default=1, help="1: capture the iteration into a CUDA graph (single-GPU default)")
@@ -352,6 +430,8 @@ def main():
     if args.impl == "reference":
         args.steps_ref = max(1, min(args.steps, 2))
         run_reference(args)
+    elif args.workload == "eval":
+        run_eval(args)
     else:
         run_ours(args)
 

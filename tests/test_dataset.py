@@ -95,3 +95,17 @@ def test_lean_batch_to_device_matches_reference_backgrounds():
     ref = torch.stack([it["background"] for it in g["items"]])
     assert torch.equal(batch["background"].cpu(), ref)
     assert batch["bbox_real"].is_cuda and "background_u8" not in batch
+
+
+def test_sampler_partition_matches_reference_streams():
+    """Rank-strided index streams equal the reference InfiniteSampler's, draw for draw (tests/golden/sampler_ref.pt)."""
+    import itertools
+    from layoutdetr_b200.training.sampler import InfiniteSampler
+    for c in golden("sampler_ref.pt"):
+        ds = list(range(c["n"]))
+        for r in range(c["world"]):
+            s = InfiniteSampler(ds, rank=r, num_replicas=c["world"], shuffle=c["shuffle"], seed=c["seed"], window_size=c["window"])
+            assert list(itertools.islice(iter(s), 120)) == c["streams"][r]
+        if not c["shuffle"]:          # the ranks' streams interleave into ONE global stream: without shuffling, 0..n-1 cyclically
+            merged = [c["streams"][p % c["world"]][p // c["world"]] for p in range(120)]
+            assert merged == [p % c["n"] for p in range(120)]

@@ -164,7 +164,7 @@ def make_tiny_layout_zip(path, seed=3):
         def put(name, arr):
             buf = io.BytesIO()
             PIL.Image.fromarray(arr).save(buf, format="PNG")
-            z.writestr(name, buf.getvalue())
+            z.writestr(zipfile.ZipInfo(name, date_time=(2023, 1, 1, 0, 0, 0)), buf.getvalue())     # fixed stamp: reproducible bytes
         for si, n in enumerate([3, 9, 1]):
             base = "page_%02d" % si
             bboxes = np.round(np.stack([rng.uniform(0.2, 0.8, n), rng.uniform(0.2, 0.8, n), rng.uniform(0.1, 0.6, n), rng.uniform(0.03, 0.2, n)], -1), 4)
@@ -177,7 +177,24 @@ def make_tiny_layout_zip(path, seed=3):
             samples.append([base, dict(bboxes=bboxes.tolist(), labels=[int(v) for v in rng.randint(0, 8, n)],
                                        texts=["text %d of page %d" % (i, si) for i in range(n)], page_label=None,
                                        attr=dict(name=base, width=W, height=H, num_bbox_labels=8))])
-        z.writestr("non_image.json", json.dumps(dict(samples=samples)))
+        z.writestr(zipfile.ZipInfo("non_image.json", date_time=(2023, 1, 1, 0, 0, 0)), json.dumps(dict(samples=samples)))
+
+
+def gen_sampler():
+    """Index streams of the reference's InfiniteSampler (torch_utils/misc.py:114-148) for several partitions."""
+    import itertools
+    from torch_utils import misc
+    _orig_init = torch.utils.data.Sampler.__init__
+    torch.utils.data.Sampler.__init__ = lambda self, *a, **k: None      # torch >= 2.x: Sampler() takes no data_source (misc.py:120 passes one)
+    out = []
+    for (n, world, seed, shuffle, window) in [(37, 4, 5, True, 0.5), (8, 2, 0, True, 0.5), (3, 1, 1, True, 0.5), (10, 3, 2, False, 0.5), (50, 8, 7, True, 0.1)]:
+        ds = list(range(n))
+        streams = [list(int(i) for i in itertools.islice(iter(misc.InfiniteSampler(ds, rank=r, num_replicas=world, shuffle=shuffle, seed=seed, window_size=window)), 120))
+                   for r in range(world)]
+        out.append(dict(n=n, world=world, seed=seed, shuffle=shuffle, window=window, streams=streams))
+    torch.utils.data.Sampler.__init__ = _orig_init
+    torch.save(out, os.path.join(GOLD, "sampler_ref.pt"))
+    print("sampler goldens:", len(out))
 
 
 def gen_dataset():
@@ -294,11 +311,13 @@ def main():
         return
     if args.only_dataset:
         gen_dataset()
+        gen_sampler()
         return
     gen_ops()
     gen_hungarian()
     gen_eval()
     gen_dataset()
+    gen_sampler()
     if args.skip_model:
         return
     torch.manual_seed(0)
