@@ -159,3 +159,17 @@ def make_inputs(batch, n_valid=8, n_slots=9, background_size=256, z_dim=4, num_b
     d = dict(z=z, bbox_class=bbox_class, bbox_real=bbox_real, bbox_text=bbox_text, bbox_patch=bbox_patch,
              padding_mask=padding_mask, background=background, c=c)
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def make_ragged_inputs(n_valid_per_sample, seed=1, **kw):
+    """Like make_inputs, but with a different number of real elements in every layout (what a real dataset batch looks like):
+    padded slots get zero boxes / class 0 / the empty string and `padding_mask` True."""
+    B = len(n_valid_per_sample)
+    d = make_inputs(B, n_valid=max(n_valid_per_sample), seed=seed, **kw)
+    N = d["padding_mask"].shape[1]
+    pad = torch.arange(N)[None, :] >= torch.tensor(list(n_valid_per_sample))[:, None]
+    d["padding_mask"] = pad
+    d["bbox_real"] = d["bbox_real"] * (~pad).unsqueeze(-1)
+    d["bbox_class"] = d["bbox_class"] * (~pad)
+    d["bbox_text"] = [[t if not bool(pad[b, n]) else "" for n, t in enumerate(row)] for b, row in enumerate(d["bbox_text"])]
+    return d

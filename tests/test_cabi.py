@@ -41,6 +41,24 @@ def test_argument_validation_without_gpu():
     assert rc == -1
 
 
+def test_new_entry_points_validate_arguments_without_gpu():
+    """Box-loss / eval-metric / loader entry points reject null pointers and bad sizes on the host, before any CUDA call."""
+    from layoutdetr_b200 import _lib
+    lib = _lib.lib()
+    i64, f32 = ctypes.c_int64, ctypes.c_float
+    assert lib.ld_layout_losses(None, None, i64(1), 9, None, None, None, None, None) == -1
+    buf = (ctypes.c_float * 64)()
+    b8 = (ctypes.c_uint8 * 64)()
+    assert lib.ld_layout_losses(buf, b8, i64(1), 65, buf, buf, None, None, None) == -1 and b"slots" in lib.ld_last_error()
+    assert lib.ld_layout_losses(buf, b8, i64(0), 9, buf, buf, None, None, None) == 0            # empty batch: nothing launched
+    assert lib.ld_giou_loss(buf, buf, i64(0), buf, None, None) == -1
+    assert lib.ld_rows_scale(buf, buf, buf, i64(4), i64(0), 0, None) == -1
+    assert lib.ld_rows_scale(buf, buf, buf, i64(0), i64(1), 0, None) == 0
+    assert lib.ld_layout_pair_metrics(buf, None, b8, i64(1), 9, buf, buf, None) == -1
+    assert lib.ld_normalize_u8_image(b8, buf, i64(1), i64(3), i64(3), buf, buf, None) == -1 and b"multiple of 4" in lib.ld_last_error()
+    assert lib.ld_cross_entropy(None, 1, i64(8), None, None, None, 1, i64(8), i64(1), 8, f32(0.0), i64(-100), f32(1.0), None, None) == -1
+
+
 def test_product_ops_refuse_cpu_tensors():
     import pytest
     import torch

@@ -69,6 +69,33 @@ def test_oracle_discriminator_matches_reference(name):
             torch.testing.assert_close(val, g["D"][key], atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))
 
 
+def test_oracle_matches_reference_on_ragged_batch():
+    """Ragged batch (1, 5 and 9 real elements of 9 slots — the empty-ish, typical and maximum cases in one batch): G and D of
+    the unmodified reference (model_b3_ragged.pt) vs the oracle; the product is checked against the oracle on the same inputs
+    on the GPU (tests/test_zz_ragged_gpu.py)."""
+    from layoutdetr_b200.synthetic import make_ragged_inputs
+    from oracle import layoutdetr_oracle as O
+    g = golden("model_b3_ragged.pt")
+    inp = make_ragged_inputs(g["ragged"], seed=g["inputs_seed"])
+    keep = ~inp["padding_mask"]
+    with torch.no_grad():
+        og = O.generator_forward(state_dict_f32(build("G")), _tok(), inp["z"], inp["bbox_class"], inp["bbox_text"], inp["padding_mask"],
+                                 inp["background"], reconst=True)
+        od = O.discriminator_forward(state_dict_f32(build("D")), _tok(), inp["bbox_real"], inp["bbox_class"], inp["bbox_text"],
+                                     inp["padding_mask"], inp["background"], reconst=True)
+    for key, val in zip(["bbox_fake", "loss_z", "logit_cls", "loss_lm", "loss_text_len"], og[:5]):
+        ref = g["G"][key]
+        if key == "bbox_fake":
+            val, ref = val[keep], ref[keep]
+        torch.testing.assert_close(val, ref, atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))
+    names = ["logit_disc", "logit_disc_uncond", "bbox_pred", "logit_cls", "loss_lm", "loss_text_len", "bg_rec", "bbox_pred_uncond", "logit_cls_uncond"]
+    for key, val in zip(names, od):
+        if key == "bg_rec":
+            torch.testing.assert_close(val[:, :, ::8, ::8], g["D"]["bg_rec_sub"], atol=1e-3, rtol=1e-3)
+        else:
+            torch.testing.assert_close(val, g["D"][key], atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))
+
+
 # ------------------------------------------------------------------------------------------------
 # evaluation sweep (SURVEY §8f rank 3): goldens in eval_ref.pt come from the reference's LayoutNet, metric functions,
 # FeatureStats and layout-FID formula (tools/gen_golden.py gen_eval)

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from layoutdetr_b200.synthetic import make_inputs, synth_state_dict  # noqa: E402
+from layoutdetr_b200.synthetic import make_inputs, make_ragged_inputs, synth_state_dict  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -222,13 +222,13 @@ def gen_dataset():
     print("dataset goldens:", out["len"], "samples, patch_shape", out["patch_shape"])
 
 
-def run_model_goldens(nd, G, D, name, batch, n_valid, seed):
-    inp = make_inputs(batch, n_valid=n_valid, seed=seed)
+def run_model_goldens(nd, G, D, name, batch, n_valid, seed, ragged=None):
+    inp = make_inputs(batch, n_valid=n_valid, seed=seed) if ragged is None else make_ragged_inputs(ragged, seed=seed)
     store = {}
     hooks = [_hook_outputs(G.text_encoder, store, "G.text_encoder"), _hook_outputs(G.input_proj, store, "G.input_proj"),
              _hook_outputs(G.transformer, store, "G.transformer"), _hook_outputs(G.fc_in, store, "G.fc_in"),
              _hook_outputs(G.backbone[0].body, store, "G.backbone_body")]
-    out = {"inputs_seed": seed, "batch": batch, "n_valid": n_valid}
+    out = {"inputs_seed": seed, "batch": batch, "n_valid": n_valid, "ragged": ragged}
     with torch.no_grad():
         t = time.time()
         res = G(inp["z"], inp["bbox_class"], inp["bbox_real"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"],
@@ -301,6 +301,7 @@ def main():
     ap.add_argument("--skip-loss", action="store_true")
     ap.add_argument("--skip-model", action="store_true")
     ap.add_argument("--only-eval", action="store_true", help="regenerate tests/golden/eval_ref.pt only")
+    ap.add_argument("--only-ragged", action="store_true", help="regenerate tests/golden/model_b3_ragged.pt only")
     ap.add_argument("--only-dataset", action="store_true", help="regenerate tests/golden/tiny_layout.zip + dataset_ref.pt only")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
@@ -325,12 +326,16 @@ def main():
     D = nd.Discriminator(**ref_shim.D_KWARGS).eval()
     synth_state_dict(G)
     synth_state_dict(D)
+    if args.only_ragged:
+        run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
+        return
     manifest = {"G": {k: list(v.shape) for k, v in G.state_dict().items()},
                 "D": {k: list(v.shape) for k, v in D.state_dict().items()}}
     with open(os.path.join(GOLD, "state_dict_manifest.json"), "w") as f:
         json.dump(manifest, f)
     run_model_goldens(nd, G, D, "model_b1_v4", batch=1, n_valid=4, seed=1)      # BASELINE configs[0]
     run_model_goldens(nd, G, D, "model_b2_v8", batch=2, n_valid=8, seed=2)
+    run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
     if not args.skip_loss:
         run_loss_goldens(nd, G, D, "loss_b2_v8", batch=2, n_valid=8, seed=2)
 
