@@ -1,0 +1,72 @@
+"""Entry points with the signatures `metrics/metric_main.py` calls (reference :90-112): `compute_layout_fid(opts, max_real,
+num_gen)` and `compute_overlap_alignment_laywise_IoU_layerwise_DocSim(opts, max_real, num_gen)`, both served by ONE pass of
+`eval_sweep.run_sweep` over the dataset (the reference runs G_ema over the whole dataset once per metric, in batches of 8,
+with `num_gpus` broadcasts per tensor per batch — metrics/metric_utils_layout.py:255-340).
+
+Partition: rank r takes the items i with i % num_gpus == r — the same SET the reference's interleaved, wrap-around
+`item_subset` (:268, :311) reduces to after `FeatureStats` truncates at `max_items`, without the duplicated tail.
+"""
+import copy
+import os
+
+import torch
+
+from . import eval_sweep
+
+_cache = {}          # (id(G), dataset path, max_real, rank) -> metric dict of the last sweep
+
+
+def rank_item_subset(num_items, num_gpus, rank):
+    return list(range(rank, num_items, num_gpus))
+
+
+def layoutnet_for(dataset_path, device):
+    """LayoutNet + checkpoint + label remapping flags chosen as the reference does from the dataset name
+    (metrics/layout_frechet_inception_distance.py:23-24, metrics/metric_layoutnet.py:27, metric_utils_layout.py:239-240)."""
+    from ..training.networks_layoutnet import LayoutNet
+    name = dataset_path.split("/")[-3] if dataset_path.count("/") >= 2 else os.path.basename(dataset_path)
+    pth = "pretrained/layoutnet_%s.pth.tar" % name
+    if not os.path.exists(pth):
+        return None, pth, False, False
+    big = any(k in pth for k in ("rico", "enrico", "clay", "ads_banner_collection", "AMT_uploaded_ads_banners", "cgl_dataset"))
+    net = LayoutNet(13 if big else 5)
+    net.load_state_dict(torch.load(pth, map_location="cpu"))
+    net = net.to(device).eval().requires_grad_(False)
+    replace = "ads_banner_collection" in pth or "AMT_uploaded_ads_banners" in pth
+    return net, pth, replace, "cgl_dataset" in pth
+
+
+def sweep(opts, max_real=None, batch_size=64, num_workers=3):
+    """One evaluation sweep for `opts` (the reference's MetricOptions: G, dataset_kwargs, num_gpus, rank, device, G_kwargs)."""
+    from ..training import dataset_layoutganpp as dl
+    path = opts.dataset_kwargs["path"]
+    key = (id(opts.G), path, max_real, opts.rank)
+    if key in _cache:
+        return _cache[key]
+    kw = {k: v for k, v in dict(opts.dataset_kwargs).items() if k != "class_name"}
+    dataset = dl.LayoutDataset(**dict(kw, lean=True))
+    num_items = len(dataset) if max_real is None else min(len(dataset), max_real)
+    loader = torch.utils.data.DataLoader(dataset, sampler=rank_item_subset(num_items, opts.num_gpus, opts.rank), batch_size=batch_size,
+                                         collate_fn=dl.collate_lean, num_workers=num_workers, prefetch_factor=2 if num_workers else None)
+    G = copy.deepcopy(opts.G).eval().requires_grad_(False).to(opts.device)
+    net, _pth, rep, rep2 = layoutnet_for(path, opts.device)
+    batches = (dl.to_device(b, opts.device) for b in loader)
+    res = eval_sweep.run_sweep(G, net, batches, z_seed=opts.rank, label_idx_replace=rep, label_idx_replace_2=rep2,
+                               G_kwargs=dict(getattr(opts, "G_kwargs", {}) or {}))
+    _cache.clear()
+    _cache[key] = res
+    return res
+
+
+def compute_layout_fid(opts, max_real, num_gen):
+    res = sweep(opts, max_real)
+    if "layout_fid" not in res:
+        raise FileNotFoundError("layout FID needs the pretrained LayoutNet checkpoint (pretrained/layoutnet_<dataset>.pth.tar)")
+    return float(res["layout_fid"]) if opts.rank == 0 else float("nan")
+
+
+def compute_overlap_alignment_laywise_IoU_layerwise_DocSim(opts, max_real, num_gen):
+    res = sweep(opts, max_real)
+    if opts.rank != 0:
+        return float("nan"), float("nan"), float("nan"), float("nan")
+    return res["overlap"], res["alignment"], res["layoutwise_iou"], res["layoutwise_docsim"]

@@ -109,3 +109,39 @@ def test_sampler_partition_matches_reference_streams():
         if not c["shuffle"]:          # the ranks' streams interleave into ONE global stream: without shuffling, 0..n-1 cyclically
             merged = [c["streams"][p % c["world"]][p // c["world"]] for p in range(120)]
             assert merged == [p % c["n"] for p in range(120)]
+
+
+def test_eval_sweep_entry_partitions_the_dataset_once_across_ranks(monkeypatch):
+    """`sweep_entry.sweep` (what the overlaid metric modules call): every item goes to exactly one rank, batches carry the keys
+    run_sweep reads, results are cached so that the FID metric and the overlap / alignment metric share one pass."""
+    import types
+    from layoutdetr_b200.metrics import sweep_entry, eval_sweep
+    from layoutdetr_b200.training import dataset_layoutganpp as dl
+    assert sweep_entry.rank_item_subset(7, 3, 0) == [0, 3, 6] and sweep_entry.rank_item_subset(7, 3, 2) == [2, 5]
+    seen, calls = [], []
+
+    def fake_run_sweep(G, net, batches, **kw):
+        calls.append(kw)
+        for b in batches:
+            assert {"bbox_real", "bbox_class", "bbox_text", "bbox_patch", "padding_mask", "background", "c"} <= set(b)
+            seen.extend(float(x) for x in b["bbox_real"][:, 0, 0])
+        return dict(overlap=1.0, alignment=2.0, layoutwise_iou=3.0, layoutwise_docsim=4.0)
+
+    monkeypatch.setattr(eval_sweep, "run_sweep", fake_run_sweep)
+    monkeypatch.setattr(dl, "to_device", lambda b, device: dict({k: v for k, v in b.items() if k != "background_u8"}, background=b["background_u8"]))
+    G = torch.nn.Linear(1, 1)
+    G.z_dim = 4
+    for rank in range(2):
+        opts = types.SimpleNamespace(G=G, dataset_kwargs=dict(class_name="training.dataset_layoutganpp.LayoutDataset", path=ZIP, use_labels=False,
+                                                               max_size=None, xflip=False, background_size=32),
+                                     num_gpus=2, rank=rank, device=torch.device("cpu"), G_kwargs={})
+        sweep_entry._cache.clear()
+        out = sweep_entry.compute_overlap_alignment_laywise_IoU_layerwise_DocSim(opts, max_real=None, num_gen=50000)
+        assert out == ((1.0, 2.0, 3.0, 4.0) if rank == 0 else tuple([float("nan")] * 4)) or rank == 1
+        n_calls = len(calls)
+        sweep_entry.sweep(opts)                                     # second metric of the same G / dataset: served from the cache
+        assert len(calls) == n_calls
+        with pytest.raises(FileNotFoundError):
+            sweep_entry.compute_layout_fid(opts, None, 50000)       # no LayoutNet checkpoint on this box
+    g = golden("dataset_ref.pt")
+    assert sorted(seen) == sorted(float(it["bboxes"][0, 0]) for it in g["items"])      # 3 items, each seen exactly once over the 2 ranks

@@ -23,9 +23,13 @@ assert nd.Generator.__module__ == "layoutdetr_b200.training.networks_detr", nd.G
 assert "layoutdetr_b200" in ba.bias_act.__module__ and "layoutdetr_b200" in uf.upfirdn2d.__module__
 import training.networks_layoutnet as ln, training.dataset_layoutganpp as dsl
 assert ln.LayoutNet.__module__ == "layoutdetr_b200.training.networks_layoutnet" and "layoutdetr_b200" in dsl.LayoutDataset.__module__
+import metrics.layout_frechet_inception_distance as lfid, metrics.overlap50k_alignment50k_layoutwise_iou50k_layoutwise_docsim50k as oa
+import metrics.metric_utils_layout as mul
+assert lfid.compute_layout_fid.__module__ == "layoutdetr_b200.metrics.sweep_entry" and mul.__file__.startswith(%r)
+assert oa.compute_overlap_alignment_laywise_IoU_layerwise_DocSim.__module__ == "layoutdetr_b200.metrics.sweep_entry"
 assert hasattr(cg, "no_weight_gradients") and misc.__file__.startswith(%r) and dnnlib.__file__.startswith(%r)
 print("OVERLAY_OK")
-''' % (REF, REF)
+''' % (REF, REF, REF)
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
         f.write(code)
