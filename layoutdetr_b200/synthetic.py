@@ -2,7 +2,7 @@
 checkpoints, no bert-base-uncased vocab and no dataset on the build / GPU boxes).
 
 Everything is a pure function of (name, shape, seed) computed with the CPU generator, so the
-reference run in the build container (tools/gen_golden.py), the CPU oracle and the CUDA path on
+reference run in the build container (tests/golden/gen_golden.py), the CPU oracle and the CUDA path on
 the GPU box all see bit-identical parameters and inputs.
 """
 import zlib

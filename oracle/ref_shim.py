@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — import the UNMODIFIED reference (/root/reference) in the build container.
 
-Only tools/gen_golden.py and oracle-pinning tests use this, and only where /root/reference exists
+Only tests/golden/gen_golden.py and oracle-pinning tests use this, and only where /root/reference exists
 (it does not exist on the GPU box).  Nothing is copied from the reference: the shims below only
 patch import-time drift between the reference's pinned deps (transformers 4.19, timm, ...) and this
 image, and replace network downloads with random init.

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt from the UNMODIFIED reference (build container only).
 
-    python tools/gen_golden.py [--skip-loss]
+    python tests/golden/gen_golden.py [--skip-loss]
 
 Imports /root/reference through oracle/ref_shim.py, overwrites every parameter/buffer with
 layoutdetr_b200.synthetic.synth_tensor(name, shape) (a pure function of the state_dict key), runs the
@@ -14,7 +14,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

@@ -1,5 +1,5 @@
 """Data loader: the LayoutDataset mirror against what the reference's own LayoutDataset returned for the
-same zip (tests/golden/tiny_layout.zip -> dataset_ref.pt, tools/gen_golden.py gen_dataset), in full and in lean mode."""
+same zip (tests/golden/tiny_layout.zip -> dataset_ref.pt, tests/golden/gen_golden.py gen_dataset), in full and in lean mode."""
 import os
 
 import numpy as np

@@ -1,5 +1,5 @@
 """CPU: pin the oracle restatement (oracle/layoutdetr_oracle.py) against outputs of the REAL reference
-(tests/golden/*.pt, produced by tools/gen_golden.py where /root/reference exists)."""
+(tests/golden/*.pt, produced by tests/golden/gen_golden.py where /root/reference exists)."""
 import os
 
 import pytest
@@ -98,7 +98,7 @@ def test_oracle_matches_reference_on_ragged_batch():
 
 # ------------------------------------------------------------------------------------------------
 # evaluation sweep: goldens in eval_ref.pt come from the reference's LayoutNet, metric functions,
-# FeatureStats and layout-FID formula (tools/gen_golden.py gen_eval)
+# FeatureStats and layout-FID formula (tests/golden/gen_golden.py gen_eval)
 # ------------------------------------------------------------------------------------------------
 def _layoutnet_sd():
     from layoutdetr_b200.synthetic import synth_state_dict
