@@ -220,6 +220,11 @@ int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float
 int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                      void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
                      float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
+/* Same contract, smaller footprint (two CTAs per SM: O re-uses S's TMEM columns, P re-uses Q's shared memory, K / V stream in
+ * 8 KB units).  ld_attention_fwd dispatches here when LD_ATTN_V2=1; experimental until verified on a B200. */
+int ld_attention_fwd_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
+                     float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout box losses of the generator objective, value + analytic gradient, one launch each.  Replace the eager

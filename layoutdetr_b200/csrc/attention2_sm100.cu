@@ -1,36 +1,29 @@
-// Fused multi-head attention forward for sm_100a:  O = softmax(Q K^T * scale + mask) V  per (batch, head, 128-query tile)
-// with <= 256 keys and head_dim <= 192 — the shapes of the LayoutDETR path: BERT text encoder / decoder (T = 256,
-// head_dim 192, additive -10000 key mask, causal for the decoder; training/med.py:146-228) and DETR self / cross
-// attention (head_dim 32, 9 / 10 / 64 keys, -inf key-padding mask; training/detr_transformer.py:208,273,277).
-//
-// One CTA per tile, warp-specialised:
-//   warp 0   TMA producer: Q tile once, then K blocks and V blocks (64 keys each) through one 4-slot smem ring
-//   warp 1   MMA issuer:   S[128 x keys] = Q K^T  (tcgen05.mma, N = 64 per key block, fp32 in TMEM columns 0..255)
-//                          O[128 x d]   += P_j V_j (A = un-normalised bf16 probabilities in smem, B = V block MN-major,
-//                                                   fp32 in TMEM columns 256..447)
-//   warp 2   TMEM allocator
-//   warps 4..11  softmax + epilogue: thread = query row (TMEM lane), two warps per lane quadrant split the key axis;
-//            sweep 1: row max (exchanged through smem), sweep 2: e = exp(s - max) -> bf16 into the swizzled smem A tile,
-//            row sums in fp32; O is normalised by 1/sum in the epilogue (flash-attention style) and written with
-//            coalesced 64-byte row segments.  Optional third sweep writes normalised P to HBM for the backward pass.
-// The fp32 score matrix and (for inference) the probabilities never touch HBM.
-#include <cstdlib>
+// Fused multi-head attention forward, variant 2 (OPT-IN: LD_ATTN_V2=1; NOT yet verified on a B200 — written after this round's
+// GPU budget was spent).  Same contract as attention_sm100.cu; what changes is the footprint,
+// so that TWO CTAs fit on an SM and the load / QK^T / softmax / PV / store phases of one tile run under those of another
+// (variant 1: one 208 KB / 512-TMEM-column CTA per SM, phases strictly back to back, tensor pipe 14 %):
+//   * 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 softmax + epilogue with ONE thread
+//     per query row over the whole key axis (no cross-warp max / sum exchange); __launch_bounds__(256, 2) -> <= 128 registers
+//   * TMEM: 256 columns; O[128 x d] re-uses the columns of S[128 x keys] once the softmax warps are done with S (the optional
+//     write of normalised P for the backward pass therefore happens BEFORE the PV MMAs are released)
+//   * shared memory: P[128 x 256] bf16 re-uses the Q tile's bytes (Q is dead when QK^T has retired); K and V stream through a
+//     ring of five 8 KB units (64 keys x 64 head-dim values = one TMA box), QK^T and PV are issued per unit (N = 64)
+//   => 64 KB + 40 KB + mask + barriers = 106.3 KB per CTA.
 #include "common.cuh"
 #include "runtime.h"
 
 namespace {
 using namespace ld;
 
-constexpr int AT_THREADS = 384;
-constexpr int AT_RING = 4;
-constexpr int AT_Q_BYTES = 3 * 16384;          // 128 x 192 bf16
-constexpr int AT_P_BYTES = 4 * 16384;          // 128 x 256 bf16
-constexpr int AT_SLOT_BYTES = 3 * 8192;        // 64 keys x 192 bf16
+constexpr int AT_THREADS = 256;
+constexpr int AT_RING = 5;                    // ring of 8 KB units
+constexpr int AT_X_BYTES = 4 * 16384;          // Q tile (128 x 192 bf16, first 48 KB) during QK^T, then P (128 x 256 bf16)
+constexpr int AT_UNIT_BYTES = 8192;            // 64 keys x 64 head-dim values (one SWIZZLE_128B TMA box)
 constexpr int AT_MASK_BYTES = 1024;            // 256 floats
-constexpr int AT_XCH_BYTES = 2 * 2 * 128 * 4;  // [max|sum][half][row]
 constexpr int AT_BAR_BYTES = 256;
-constexpr int AT_SMEM = AT_Q_BYTES + AT_P_BYTES + AT_RING * AT_SLOT_BYTES + AT_MASK_BYTES + AT_XCH_BYTES + AT_BAR_BYTES + 1024;
-constexpr uint32_t TM_S = 0, TM_O = 256;
+constexpr int AT_SMEM = AT_X_BYTES + AT_RING * AT_UNIT_BYTES + AT_MASK_BYTES + AT_BAR_BYTES + 1024;
+constexpr uint32_t TM_COLS = 256, TM_S = 0, TM_O = 0;       // O aliases S
+static_assert(2 * (AT_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
 
 struct AttnParams {
     int B, H, Lq, Lk, d;
@@ -42,17 +35,16 @@ struct AttnParams {
     __nv_bfloat16* P; long ldp;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_s = smem;
-    uint8_t* p_s = q_s + AT_Q_BYTES;
-    uint8_t* ring = p_s + AT_P_BYTES;
-    float* mask_s = reinterpret_cast<float*>(ring + AT_RING * AT_SLOT_BYTES);
-    float* xch = mask_s + 256;                                   // [2 kinds][2 halves][128 rows]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch) + AT_XCH_BYTES);
+    uint8_t* p_s = smem;                                         // same bytes, later in time
+    uint8_t* ring = smem + AT_X_BYTES;
+    float* mask_s = reinterpret_cast<float*>(ring + AT_RING * AT_UNIT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mask_s) + AT_MASK_BYTES);
     uint64_t* full_bar = bars;            // [AT_RING]
     uint64_t* empty_bar = bars + AT_RING; // [AT_RING]
     uint64_t* q_bar = bars + 2 * AT_RING;
@@ -71,12 +63,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < AT_RING; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(q_bar, 1); mbar_init(s_bar, 1); mbar_init(p_bar, 8); mbar_init(o_bar, 1);
+        mbar_init(q_bar, 1); mbar_init(s_bar, 1); mbar_init(p_bar, 4); mbar_init(o_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-    if (warp >= 4) {                                             // additive key mask of this batch element
-        const int c = threadIdx.x - 128;
+    if (warp == 2) { tmem_alloc(tmem_slot, TM_COLS); tmem_relinquish(); }
+    {                                                            // additive key mask of this batch element (all 256 threads)
+        const int c = threadIdx.x;
         const uint8_t* km = p.key_mask ? p.key_mask + (long)b * p.Lk : nullptr;
         mask_s[c] = (c < p.Lk) ? ((km && km[c]) ? p.mask_value : 0.0f) : -INFINITY;    // keys beyond Lk never attend
     }
@@ -84,7 +76,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int slot_bytes = p.dch * 8192;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -94,11 +85,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int pass = 0; pass < 2; ++pass) {               // pass 0: K blocks, pass 1: V blocks
                 const CUtensorMap* tm = pass == 0 ? &tmK : &tmV;
                 for (int j = 0; j < p.nkv; ++j) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], slot_bytes);
-                    uint8_t* dst = ring + stage * AT_SLOT_BYTES;
-                    for (int c = 0; c < p.dch; ++c) tma_load_4d(dst + c * 8192, tm, &full_bar[stage], c * 64, j * 64, h, b);
-                    if (++stage == AT_RING) { stage = 0; phase ^= 1; }
+                    for (int c = 0; c < p.dch; ++c) {            // one 8 KB unit = one ring slot
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], AT_UNIT_BYTES);
+                        tma_load_4d(ring + stage * AT_UNIT_BYTES, tm, &full_bar[stage], c * 64, j * 64, h, b);
+                        if (++stage == AT_RING) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -106,60 +98,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
-            const uint32_t idesc_o = make_idesc_bf16(128, p.dch * 64, 0, 1);
+            const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
             mbar_wait(q_bar, 0);
             tc_fence_after();
             const uint32_t qa = smem_u32(q_s);
-            for (int j = 0; j < p.nkv; ++j) {                    // S[:, 64j : 64j+64] = Q K_j^T
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t kb = smem_u32(ring + stage * AT_SLOT_BYTES);
+            for (int j = 0; j < p.nkv; ++j) {                    // S[:, 64j : 64j+64] = Q K_j^T, one head-dim chunk per unit
                 for (int c = 0; c < p.dch; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t kb = smem_u32(ring + stage * AT_UNIT_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t da = make_smem_desc(qa + c * 16384 + kk * 32, 16, 1024);
-                        const uint64_t db = make_smem_desc(kb + c * 8192 + kk * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc(kb + kk * 32, 16, 1024);
                         umma_bf16_ss(tmem_base + TM_S + 64 * j, da, db, idesc_s, (c > 0 || kk > 0) ? 1u : 0u);
                     }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == AT_RING) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (++stage == AT_RING) { stage = 0; phase ^= 1; }
             }
             umma_commit(s_bar);                                  // scores complete -> softmax warps
-            mbar_wait(p_bar, 0);                                 // probabilities are in smem
+            mbar_wait(p_bar, 0);                                 // probabilities are in smem (over Q) and S is dead
             tc_fence_after();
             const uint32_t pa = smem_u32(p_s);
-            for (int j = 0; j < p.nkv; ++j) {                    // O += P[:, 64j : 64j+64] V_j
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t vb = smem_u32(ring + stage * AT_SLOT_BYTES);
+            for (int j = 0; j < p.nkv; ++j) {                    // O[:, 64c : 64c+64] += P[:, 64j : 64j+64] V_j[:, 64c : 64c+64]
+                for (int c = 0; c < p.dch; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t vb = smem_u32(ring + stage * AT_UNIT_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t da = make_smem_desc(pa + j * 16384 + kk * 32, 16, 1024);
-                    const uint64_t db = make_smem_desc(vb + kk * 2048, 8192, 1024);
-                    umma_bf16_ss(tmem_base + TM_O, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t da = make_smem_desc(pa + j * 16384 + kk * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc(vb + kk * 2048, 8192, 1024);
+                        umma_bf16_ss(tmem_base + TM_O + 64 * c, da, db, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == AT_RING) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (++stage == AT_RING) { stage = 0; phase ^= 1; }
             }
             umma_commit(o_bar);
         }
     } else if (warp >= 4) {
-        const int e = warp - 4, q = e & 3, half = e >> 2;
+        const int e = warp - 4, q = e;                           // warp 4 + q owns TMEM lanes 32q .. 32q+31
         const int r = q * 32 + lane;                             // query row within the tile == TMEM lane
         const int row = m0 + r;
         const bool row_ok = row < p.Lq;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        // key blocks of this warp's half
-        const int jb = half == 0 ? 0 : (p.nkv + 1) / 2;
-        const int je = half == 0 ? (p.nkv + 1) / 2 : p.nkv;
+        const int jb = 0, je = p.nkv;                            // every key block: one thread owns its query row
         const uint32_t mask_a = smem_u32(mask_s);          // shared-space addresses (LDS / STS instead of generic LD / ST)
-        const uint32_t xmax_a = smem_u32(xch);             // [2][128]
-        const uint32_t xsum_a = xmax_a + 1024;             // [2][128]
         const uint32_t p_a = smem_u32(p_s);
         mbar_wait(s_bar, 0);
         tc_fence_after();
-        // ---- sweep 1: row max over this half's keys
+        // ---- sweep 1: row max
         float mx = -INFINITY;
         for (int j = jb; j < je; ++j) {
 #pragma unroll
@@ -182,9 +172,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
             }
         }
-        sts_f32(xmax_a + (half * 128 + r) * 4, mx);
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        mx = fmaxf(lds_f32(xmax_a + r * 4), lds_f32(xmax_a + (128 + r) * 4));
         // ---- sweep 2: e = exp(s - max) -> bf16 into the swizzled A tile; fp32 row sum
         float sum = 0.f;
         for (int j = jb; j < je; ++j) {
@@ -219,12 +206,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
             }
         }
-        sts_f32(xsum_a + (half * 128 + r) * 4, sum);
-        fence_proxy_async_smem();                                // generic-proxy smem writes -> visible to tcgen05.mma
-        tc_fence_before();
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (lane == 0) mbar_arrive(p_bar);
-        const float inv = __fdividef(1.0f, lds_f32(xsum_a + r * 4) + lds_f32(xsum_a + (128 + r) * 4));
+        const float inv = __fdividef(1.0f, sum);
         // ---- optional sweep 3: normalised probabilities to HBM (needed by the backward pass)
         if (p.P != nullptr) {
             __nv_bfloat16* prow_g = p.P + ((long)(b * p.H + h) * p.Lq + row) * p.ldp;
@@ -258,12 +240,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
             }
         }
+        // ---- P is in shared memory and nobody reads S any more: release the PV MMAs (they overwrite S's columns with O)
+        fence_proxy_async_smem();                                // generic-proxy smem writes -> visible to tcgen05.mma
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_bar);
         // ---- epilogue: O * (1 / sum) -> bf16, coalesced 64-byte row segments through a swizzled smem tile
         mbar_wait(o_bar, 0);
         tc_fence_after();
         const uint32_t stg_a = p_a + e * 2048;                   // P tile is dead once the PV MMAs have retired
         const int sw_w = (lane >> 1) & 3, pc = lane & 3;
-        const int cbeg = half * p.dch * 32, cend = cbeg + p.dch * 32;
+        const int cbeg = 0, cend = p.dch * 64;
         __nv_bfloat16* obase = p.O + (long)b * p.Lq * p.ldo + (long)h * p.d;
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
             if (c0 >= p.d) break;                                // warp-uniform: padding columns of head_dim < 64
@@ -298,7 +285,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, TM_COLS);
 }
 
 int make_map(CUtensorMap* tm, const void* ptr, int64_t ld_, int d, int L, int H, int B, uint32_t box_rows) {
@@ -312,15 +299,12 @@ int make_map(CUtensorMap* tm, const void* ptr, int64_t ld_, int d, int L, int H,
 }
 }  // namespace
 
-// q / k / v point at column 0 of head 0 inside row-major [B*L, ld] bf16 buffers (head h at columns h*d .. h*d+d).
-extern "C" int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+// Same contract as ld_attention_fwd.  q / k / v point at column 0 of head 0 inside row-major [B*L, ld] bf16 buffers (head h at columns h*d .. h*d+d).
+extern "C" int ld_attention_fwd_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                 void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
                                 float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream) {
     using namespace ld;
-    // opt-in two-CTAs-per-SM variant (attention2_sm100.cu); off unless LD_ATTN_V2=1 — it has not run on a B200 yet
-    static const int env_v2 = [] { const char* e = getenv("LD_ATTN_V2"); return e ? atoi(e) : 0; }();
-    if (env_v2) return ld_attention_fwd_v2(q, ldq, k, ldk, v, ldv, o, ldo, p_out, ldp, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal, stream);
-    LD_CHECK_ARG(q && k && v && o && B > 0 && H > 0 && Lq > 0 && Lk > 0, "attention_fwd: bad argument");
+    LD_CHECK_ARG(q && k && v && o && B > 0 && H > 0 && Lq > 0 && Lk > 0, "attention_fwd_v2: bad argument");
     LD_CHECK_ARG(Lk <= 256 && d <= 192 && d % 8 == 0, "attention_fwd: needs <= 256 keys and head_dim <= 192 (multiple of 8); got Lk=%d d=%d", Lk, d);
     LD_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)o & 15) == 0 && (!p_out || (ldp % 8 == 0 && ((uintptr_t)p_out & 15) == 0)),
                  "attention_fwd: output alignment");
@@ -336,13 +320,16 @@ extern "C" int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64
     e = make_map(&tmV, v, ldv, d, Lk, H, B, 64); if (e) return e;
     static bool attr_set = false;
     if (!attr_set) {
-        int s = cuda_status(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM), "attention: smem attr");
+        int s = cuda_status(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM), "attention v2: smem attr");
+        if (s) return s;
+        s = cuda_status(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                        "attention v2: carveout");
         if (s) return s;
         attr_set = true;
     }
     const long grid = (long)B * H * p.q_tiles;
-    attention_fwd_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    attention_fwd_v2_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     count_launch();
-    LD_LAUNCH_CHECK("attention_fwd");
+    LD_LAUNCH_CHECK("attention_fwd_v2");
     return 0;
 }
