@@ -190,3 +190,48 @@ def test_eval_sweep_exchange_step_two_ranks_gloo(tmp_path):
     cov = [x[i].T @ x[i] / 40 - __import__("numpy").outer(mean[i], mean[i]) for i in range(2)]
     ref = O.layout_fid(mean[1], cov[1], mean[0], cov[0])
     assert abs(res["layout_fid"] - ref) <= 1e-9 * max(1.0, abs(ref))
+
+
+def test_box_loss_arithmetic_edge_cases_match_oracle_autograd():
+    """Ties and degenerate geometry, where autograd's conventions matter (max / min ties split evenly, first minimum wins,
+    nan_to_num / masked_fill stop gradients): all-zero padded slots (the dataset's convention), duplicated boxes, shared
+    edges, a box nested in another, a single valid slot.  Two degenerate inputs are NOT reproduced and never occur on the path
+    (boxes are sigmoid outputs, every layout has >= 1 element): a valid box of zero area (reference gradient: NaN, here 0 for
+    the 0/0 terms) and a layout without any valid slot (value NaN in both; reference gradient 0, here NaN)."""
+    import ctypes
+    from oracle import layoutdetr_oracle as O
+    lib = _host_box_lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    g = torch.Generator().manual_seed(1)
+    base = torch.rand((2, 9, 4), generator=g) * 0.4 + 0.2
+    mask6 = torch.ones(2, 9, dtype=torch.bool)
+    mask6[:, 6:] = False
+    single = torch.zeros(2, 9, dtype=torch.bool)
+    single[:, 0] = True
+    cases = []
+    b = base.clone(); b[:, 6:] = 0; cases.append((b, mask6))
+    b = base.clone(); b[:, 1] = b[:, 0]; cases.append((b, mask6))
+    b = base.clone(); b[:, 1, 0] = b[:, 0, 0]; b[:, 1, 2] = b[:, 0, 2]; cases.append((b, mask6))
+    b = base.clone(); b[:, 1] = torch.tensor([0.5, 0.5, 0.1, 0.05]); b[:, 0] = torch.tensor([0.5, 0.5, 0.4, 0.3]); cases.append((b, mask6))
+    cases.append((base.clone(), single))
+    for bbox, mask in cases:
+        B, N, _ = bbox.shape
+        ref = bbox.clone().requires_grad_(True)
+        ov, al = O.compute_overlap(ref, mask), O.compute_alignment(ref, mask)
+        (ov.sum() + al.sum()).backward()
+        bb, v8 = bbox.contiguous(), mask.to(torch.uint8).contiguous()
+        o, a, jo, ja = torch.empty(B), torch.empty(B), torch.empty(B, N, 4), torch.empty(B, N, 4)
+        lib.host_layout_losses(P(bb), P(v8), ctypes.c_long(B), N, P(o), P(a), P(jo), P(ja))
+        torch.testing.assert_close(o, ov.detach(), atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(a, al.detach(), atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(jo + ja, ref.grad, atol=5e-6, rtol=1e-4)
+    f = base[0, :6].clone().contiguous()
+    r = f.clone()
+    r[:3] += 0.05                                                    # rows 3..5: fake == real exactly (every max / min is a tie)
+    fr = f.clone().requires_grad_(True)
+    ref = O.generalized_iou_loss(fr, r)
+    ref.backward()
+    lo, jf = torch.empty(1), torch.empty(6, 4)
+    lib.host_giou_loss(P(f), P(r), ctypes.c_long(6), P(lo), P(jf))
+    torch.testing.assert_close(lo[0], ref.detach(), atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(jf, fr.grad, atol=1e-6, rtol=1e-4)
