@@ -264,6 +264,17 @@ def run_model_goldens(nd, G, D, name, batch, n_valid, seed, ragged=None):
     print("saved", name)
 
 
+def run_generator_1024(nd, G, name="model_b1_bg1024", seed=21):
+    """BASELINE configs[3] geometry: a 1024 x 1024 background -> 32 x 32 = 1024 image tokens; G.forward only (eval)."""
+    inp = make_inputs(1, n_valid=8, seed=seed, background_size=1024)
+    with torch.no_grad():
+        t = time.time()
+        out = G(inp["z"], inp["bbox_class"], inp["bbox_real"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"], inp["background"], inp["c"])
+        print(name, "G fwd %.1fs" % (time.time() - t))
+    torch.save({"inputs_seed": seed, "batch": 1, "n_valid": 8, "background_size": 1024, "bbox_fake": out.clone()}, os.path.join(GOLD, name + ".pt"))
+    print("saved", name)
+
+
 def run_loss_goldens(nd, G, D, name, batch, n_valid, seed):
     """Full reference loss + backward (training/loss.py accumulate_gradients) with dropout off."""
     import training.loss as ref_loss
@@ -328,6 +339,7 @@ def main():
     synth_state_dict(D)
     if args.only_ragged:
         run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
+        run_generator_1024(nd, G)
         return
     manifest = {"G": {k: list(v.shape) for k, v in G.state_dict().items()},
                 "D": {k: list(v.shape) for k, v in D.state_dict().items()}}
@@ -336,6 +348,7 @@ def main():
     run_model_goldens(nd, G, D, "model_b1_v4", batch=1, n_valid=4, seed=1)      # BASELINE configs[0]
     run_model_goldens(nd, G, D, "model_b2_v8", batch=2, n_valid=8, seed=2)
     run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
+    run_generator_1024(nd, G)
     if not args.skip_loss:
         run_loss_goldens(nd, G, D, "loss_b2_v8", batch=2, n_valid=8, seed=2)
 

@@ -96,6 +96,19 @@ def test_oracle_matches_reference_on_ragged_batch():
             torch.testing.assert_close(val, g["D"][key], atol=3e-4, rtol=3e-4, msg=lambda m: "%s: %s" % (key, m))
 
 
+def test_oracle_generator_matches_reference_at_1024_background():
+    """BASELINE configs[3] geometry (1024 x 1024 background -> 1024 image tokens): G.forward of the reference vs the oracle."""
+    from layoutdetr_b200.synthetic import make_inputs
+    from oracle import layoutdetr_oracle as O
+    g = golden("model_b1_bg1024.pt")
+    inp = make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"], background_size=g["background_size"])
+    with torch.no_grad():
+        out = O.generator_forward(state_dict_f32(build("G")), _tok(), inp["z"], inp["bbox_class"], inp["bbox_text"], inp["padding_mask"],
+                                  inp["background"])
+    keep = ~inp["padding_mask"]
+    torch.testing.assert_close(out[keep], g["bbox_fake"][keep], atol=3e-4, rtol=3e-4)
+
+
 # ------------------------------------------------------------------------------------------------
 # evaluation sweep (SURVEY §8f rank 3): goldens in eval_ref.pt come from the reference's LayoutNet, metric functions,
 # FeatureStats and layout-FID formula (tests/golden/gen_golden.py gen_eval)

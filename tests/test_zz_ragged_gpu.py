@@ -41,3 +41,19 @@ def test_generator_and_discriminator_on_ragged_batch_match_oracle():
     for k in ("logit_disc", "logit_disc_uncond", "logit_cls", "logit_cls_uncond"):
         assert float((o[k] - r[k]).abs().max()) < 5e-2 * max(1.0, float(r[k].abs().max())), k
     assert abs(float(o["loss_lm"]) - float(r["loss_lm"])) < 2e-2 * float(r["loss_lm"])
+
+
+@pytest.mark.xfail(strict=False, reason="1024-token path (keys > 256: GEMM + softmax kernel instead of the fused attention) was added to the "
+                                        "suite after this round's GPU budget was spent; not yet run on a B200")
+def test_generator_at_1024_background_matches_reference_golden():
+    """BASELINE configs[3] geometry: 1024 x 1024 background, 32 x 32 image tokens (golden from the reference, oracle pinned on CPU)."""
+    from helpers import golden
+    from layoutdetr_b200.synthetic import make_inputs
+    g = golden("model_b1_bg1024.pt")
+    inp = make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"], background_size=g["background_size"])
+    G = build("G").cuda()
+    d = _dev(inp)
+    with torch.no_grad():
+        out = G(d["z"], d["bbox_class"], d["bbox_real"], d["bbox_text"], d["bbox_patch"], d["padding_mask"], d["background"], d["c"]).float().cpu()
+    keep = ~inp["padding_mask"]
+    assert float((out - g["bbox_fake"])[keep].abs().max()) < BOX_TOL
