@@ -47,7 +47,8 @@ def sweep(opts, max_real=None, batch_size=64, num_workers=3):
     dataset = dl.LayoutDataset(**dict(kw, lean=True))
     num_items = len(dataset) if max_real is None else min(len(dataset), max_real)
     loader = torch.utils.data.DataLoader(dataset, sampler=rank_item_subset(num_items, opts.num_gpus, opts.rank), batch_size=batch_size,
-                                         collate_fn=dl.collate_lean, num_workers=num_workers, prefetch_factor=2 if num_workers else None)
+                                         collate_fn=dl.collate_lean, num_workers=num_workers, prefetch_factor=2 if num_workers else None,
+                                         pin_memory=torch.cuda.is_available())
     G = copy.deepcopy(opts.G).eval().requires_grad_(False).to(opts.device)
     net, _pth, rep, rep2 = layoutnet_for(path, opts.device)
     batches = (dl.to_device(b, opts.device) for b in loader)

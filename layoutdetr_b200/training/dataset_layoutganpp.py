@@ -248,7 +248,7 @@ class LayoutDataset(Dataset):
 
 # ---------------------------------------------------------------------------------------------------------------------
 def collate_lean(items):
-    """DataLoader collate for `lean=True` items: uint8 backgrounds stacked into ONE pinned buffer, texts transposed into the
+    """DataLoader collate for `lean=True` items: uint8 backgrounds stacked into ONE buffer, texts transposed into the
     list-of-lists the networks take (the reference transposes after the default collate, training_loop.py:259)."""
     samples = [it[0] for it in items]
     B = len(samples)
@@ -262,11 +262,7 @@ def collate_lean(items):
         background_u8=bg,
         c=torch.from_numpy(np.stack([it[1] for it in items])),
     )
-    if torch.cuda.is_available():
-        for k, v in out.items():
-            if torch.is_tensor(v):
-                out[k] = v.pin_memory()
-    return out
+    return out          # pinning is the DataLoader's job (`pin_memory=True`: done in the parent process, never in a forked worker)
 
 
 def to_device(batch, device):
