@@ -18,6 +18,19 @@ def test_header_declares_entry_points():
     assert "ld_gemm_bf16" in names and "ld_bias_act" in names and "ld_upfirdn2d" in names and len(names) >= 30
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 on its own (no C++ / CUDA / torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc on this box")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "layoutdetr_sm100.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_library_builds_and_exports_all_declared_symbols():
     from layoutdetr_b200 import build
     lib_path = build.build(verbose=False)
