@@ -125,38 +125,58 @@ def run_eval(args):
     """`--workload eval` (BASELINE configs[4]): the evaluation sweep — G_ema forward at 64 layouts per
     batch, LayoutNet features of real and generated layouts, overlap / alignment / layout-wise IoU / DocSim, FID — through
     layoutdetr_b200.metrics.eval_sweep.run_sweep with host batches (H2D inside the timed region, D2H of the metric dict),
-    next to the CPU oracle of the same sweep on a bounded sample.  Single GPU; one JSON line."""
+    next to the CPU oracle of the same sweep on a bounded sample.  Under torchrun every rank sweeps its own shard (weak scaling)
+    and the statistics meet in the sweep's single all-reduce; rank 0 prints one JSON line."""
     import torch
     from layoutdetr_b200 import _lib
     from layoutdetr_b200.synthetic import SyntheticTokenizer, make_inputs
     from layoutdetr_b200.training import networks_detr as nd
     from layoutdetr_b200.training.networks_layoutnet import LayoutNet
     from layoutdetr_b200.metrics import eval_sweep
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)      # the sweep's one exchange: all-reduce of the running statistics
     _lib.lib()
     torch.manual_seed(0)
     G = nd.Generator(**G_KWARGS).to(dev).eval().requires_grad_(False)
     net = LayoutNet(13).to(dev).eval().requires_grad_(False)
     B, nb = args.eval_batch, max(1, args.steps)
-    host = [make_inputs(B, n_valid=8, seed=50 + i) for i in range(nb)]
+    host = [make_inputs(B, n_valid=8, seed=50 + 1000 * rank + i) for i in range(nb)]      # every rank sweeps its own shard of the layouts
     for hb in host:
         for k, v in hb.items():
             if torch.is_tensor(v):
                 hb[k] = v.pin_memory()
     to_dev = lambda hb: {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(max(1, args.warmup)):
         eval_sweep.run_sweep(G, net, [to_dev(host[0])])                  # tokeniser cache, weight shadows
-    torch.cuda.synchronize()
+    sync_all()
     _lib.launch_count_reset()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     t0 = time.perf_counter()
-    res = eval_sweep.run_sweep(G, net, (to_dev(hb) for hb in host))     # one sweep over `steps` batches
-    torch.cuda.synchronize()
+    res = eval_sweep.run_sweep(G, net, (to_dev(hb) for hb in host))     # one sweep over `steps` batches per rank (+ the final all-reduce)
+    sync_all()
     sec = time.perf_counter() - t0
     clocks = sampler.stop()
-    n = B * nb
+    if world > 1:
+        tsec = torch.tensor([sec], device=dev)
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        sec = float(tsec.item())
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n = B * nb * world
     h2d = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
     cpu = None
     if not args.no_cpu_baseline:
@@ -179,14 +199,14 @@ def run_eval(args):
                    sample="%d layouts, oracle sweep (%.1f s)" % (args.cpu_sample, cpu_sec))
     gf = 425.2                                                           # G.forward(reconst=False) GFLOP per sample
     line = dict(metric="eval-sweep layouts/sec (G_ema fwd + LayoutNet features + overlap/alignment/IoU/DocSim + layout FID)",
-                value=n / sec, unit="layouts/s", n_gpus=1, steps=nb, warmup=args.warmup, ms_per_step=sec / nb * 1e3, higher_is_better=True,
+                value=n / sec, unit="layouts/s", n_gpus=world, steps=nb, warmup=args.warmup, ms_per_step=sec / nb * 1e3, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload="eval sweep, %d layouts per batch, 256x256 backgrounds, 8 of 9 slots (BASELINE configs[4] shapes)" % B,
                             batch_per_gpu=B, l2="inputs larger than L2 per batch (text activations 680 MB)", timing="host clock around the public API call"),
                 clocks=clocks, e2e=dict(value=n / sec, unit="layouts/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=8 * 6),
                 gpu_launches=int(_lib.launch_count()),
-                roofline=dict(bound="tensor", achieved=n / sec * gf / 1e3, peak=peaks()["sustained"], unit="TFLOP/s",
-                              frac=n / sec * gf / 1e3 / peaks()["sustained"], traffic=None, gflop_per_layout=gf,
+                roofline=dict(bound="tensor", achieved=n / sec * gf / 1e3 / world, peak=peaks()["sustained"], unit="TFLOP/s (per GPU)",
+                              frac=n / sec * gf / 1e3 / world / peaks()["sustained"], traffic=None, gflop_per_layout=gf,
                               note="whole sweep against the algorithmic forward FLOPs (dense reference shapes)"),
                 cpu_baseline=cpu, result=res)
     print(json.dumps(line), flush=True)
