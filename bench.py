@@ -275,6 +275,8 @@ def run_ours(args):
     for m in (G, D):
         m.text_trim = args.text_trim
         m.text_dedup = args.text_dedup
+        # the reference trains G / D in .train() (training_loop.py:133-134): DETR + BERT dropout 0.1 live, also in the frozen encoder
+        m.train(bool(args.dropout))
     trainer = Trainer(G, D, dev, batch_size=B * world, num_gpus=world)
 
     # ---- inputs: resident (value) and host-pinned rotating batches (e2e)
@@ -410,7 +412,8 @@ def run_ours(args):
                     config=dict(workload="bs16 256x256 synthetic, 8 of 9 slots, G+D fwd/bwd + Adam + EMA (BASELINE configs[1])",
                                 batch_per_gpu=B, global_batch=B * world, text_tokens=256, text_trim=bool(args.text_trim),
                                 text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
-                                dropout="off (deterministic eval-semantics kernels)", parallelism="dp%d" % world,
+                                dropout=("on (train mode: DETR 0.1, BERT hidden / attention 0.1, in-kernel Philox)" if args.dropout
+                                         else "off (modules in .eval(): deterministic kernels)"), parallelism="dp%d" % world,
                                 launch="cuda graph replay of the captured iteration" if gs is not None else "eager (one launch per kernel)",
                                 lanes=dict(level=LANES.level, text_ctas=LANES.text_ctas, lm_ctas=LANES.lm_ctas, priority=LANES.high_priority,
                                            note="independent sub-graphs of the iteration on parallel streams (same kernels, same operands)")),
@@ -436,6 +439,7 @@ def main():
     ap.add_argument("--eval-batch", type=int, default=64)
     ap.add_argument("--text-trim", type=int, default=0, help="1: drop all-padding token columns (exact)")
     ap.add_argument("--text-dedup", type=int, default=0, help="1: reuse frozen text-encoder features across the 5 calls (exact)")
+    ap.add_argument("--dropout", type=int, default=1, help="1 (default): G / D in .train() as the reference's loop, dropout live; 0: .eval()")
     ap.add_argument("--graph", type=int, default=1, help="1: capture the iteration into a CUDA graph (single-GPU default)")
     ap.add_argument("--variants", type=int, default=1, help="1: also time the exact work-saving variant (reported separately)")
     ap.add_argument("--lanes", type=int, default=None, help="lane scheduler level 0..3 (layoutdetr_b200/lanes.py); default: LD_LANES or 3")

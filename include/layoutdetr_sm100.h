@@ -151,6 +151,21 @@ int ld_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* x, 
                      void* dx_bf16, float* dx_f32, int64_t lddx, float* dgamma, float* dbeta,
                      int rows, int C, void* stream);
 
+/* y = LayerNorm(dropout(x) + res) with the Philox mask of (rng_state, rng_site), group = row * C/8 + column/8 (the element order
+ * of ld_dropout on the contiguous [rows, C] tensor); pre_f32 (optional) = dropout(x) + res for ld_layernorm_bwd.  Hidden-state
+ * dropout of the post-norm residual blocks: training/med.py:237-242,318-325, training/detr_transformer.py:210-214,270-285.
+ * bf16 x / res / y, C % 256 == 0. */
+int ld_layernorm_res_dropout_fwd(const void* x_bf16, int64_t ldx, const void* res_bf16, int64_t ldr,
+                                 const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* pre_f32, int64_t ldpre,
+                                 float* mean, float* rstd, int rows, int C, float eps,
+                                 float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
+/* Dropout randomness (nn.Dropout sites of training/med.py:96,213,240,318, training/detr_transformer.py:185-194): Philox4x32-10,
+ * key = 64-bit seed, counter = (group lo, group hi, site, step), eight 16-bit lanes per group, element dropped when its lane <
+ * round(p * 65536).  rng_state: device uint32[4] {seed_lo, seed_hi, step, 0}.  ld_rng_advance: step += 1 (once per iteration,
+ * graph-capturable).  ld_dropout: y = keep ? x / (1 - p) : 0 on a contiguous tensor (n % 8 == 0), group = index / 8; x may alias y. */
+int ld_rng_advance(uint32_t* rng_state, void* stream);
+int ld_dropout(const void* x, void* y, int dtype, int64_t n, float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
+
 /* BERT embeddings: y = LayerNorm(word[ids[r]] + pos[r % T]) (training/med.py:74-97) and the scatter-add of its
  * gradient into the (fp32) embedding tables; rows with ids == pad_id get no word gradient (padding_idx). */
 int ld_embed_ln_fwd(const int64_t* ids, const float* word, const float* pos, const float* gamma, const float* beta,
@@ -212,17 +227,33 @@ int ld_adam_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int
                  void* stream);
 int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float beta, void* stream);
 
-/* Fused multi-head attention forward (QK^T -> scale + mask -> softmax -> PV in one kernel, scores / probabilities stay
- * on chip) for <= 256 keys and head_dim <= 192: BertSelfAttention.forward (training/med.py:146-228) and
- * nn.MultiheadAttention as called by training/detr_transformer.py:208,273,277.  q / k / v: bf16 row-major [B*L, ld] buffers,
- * head h in columns h*d .. h*d+d of the given base; o: bf16 [B*Lq, ldo]; p_out (optional, for the backward pass): bf16
- * [B*H, Lq, ldp] normalised probabilities.  key_mask [B, Lk] (1 = masked) adds -10000 (mask_inf = 0) or -inf. */
+/* Fused multi-head attention forward (QK^T -> scale + mask -> softmax -> dropout -> PV in one persistent kernel, scores /
+ * probabilities stay on chip) for <= 256 keys and head_dim <= 192: BertSelfAttention.forward (training/med.py:146-228, dropout
+ * :213) and nn.MultiheadAttention as called by training/detr_transformer.py:208,273,277.  q / k / v: bf16 row-major [B*L, ld]
+ * buffers, head h in columns h*d .. h*d+d of the given base; o: bf16 [B*Lq, ldo].  key_mask [B, Lk] (1 = masked) adds -10000
+ * (mask_inf = 0) or -inf.  For the backward pass: lse_out (optional) fp32 [B*H, Lq] = log2-domain log-sum-exp of the scaled +
+ * masked scores (max2 + log2(sum 2^(s2 - max2)), s2 = s * log2 e), consumed by ld_attention_bwd; p_out (optional, legacy) bf16
+ * [B*H, Lq, ldp] normalised probabilities.  dropout_p > 0: probabilities are dropped with the Philox mask of
+ * (rng_state = device {seed_lo, seed_hi, step, 0}, rng_site), element (b, h, row, col) -> group ((b*H+h)*Lq+row)*32 + col/8. */
 int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                     void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
-                     float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
-/* Same contract, smaller footprint (two CTAs per SM: O re-uses S's TMEM columns, P re-uses Q's shared memory, K / V stream in
- * 8 KB units).  ld_attention_fwd dispatches here when LD_ATTN_V2=1; experimental until verified on a B200. */
-int ld_attention_fwd_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     void* o, int64_t ldo, void* p_out, int64_t ldp, float* lse_out,
+                     int B, int H, int Lq, int Lk, int d, float scale, const uint8_t* key_mask, int mask_inf, int causal,
+                     float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
+/* Fused attention backward, the adjoint of ld_attention_fwd (same shape limits, same mask / dropout arguments): recomputes the
+ * probabilities from lse (the forward's lse_out), regenerates the dropout mask and produces
+ *   dq      bf16 [B*Lq, lddq] at head h columns h*d..   dQ = dS K,  dS = P o (dropout'(dO V^T) - rowsum(dO o O)) * scale
+ *   pd_out  bf16 [B*H, Lq, ldp]  dropout(P)   (left operand of dV = Pd^T dO)
+ *   ds_out  bf16 [B*H, Lq, ldp]  dS           (left operand of dK = dS^T Q)
+ * in one kernel (scores, dO V^T and dQ accumulate in TMEM).  o / d_o: forward output and its gradient, bf16 [B*Lq, ldo].  The two
+ * transposed products stay batched ld_gemm_bf16 calls.  Replaces autograd of training/med.py:183-215 and of
+ * F.multi_head_attention_forward (training/detr_transformer.py:208,273,277). */
+int ld_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                     const void* o, const void* d_o, int64_t ldo, const float* lse,
+                     void* dq, int64_t lddq, void* pd_out, void* ds_out, int64_t ldp,
+                     int B, int H, int Lq, int Lk, int d, float scale, const uint8_t* key_mask, int mask_inf, int causal,
+                     float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
+/* Round-1 kernel (one tile per CTA, no overlap between phases); ld_attention_fwd dispatches here when LD_ATTN_V1=1 (A/B only). */
+int ld_attention_fwd_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                      void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
                      float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream);
 

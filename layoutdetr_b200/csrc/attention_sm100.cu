@@ -1,3 +1,4 @@
+// ROUND-1 KERNEL, kept only as the A/B baseline of attention_fwd_sm100.cu (LD_ATTN_V1=1): one tile per CTA, phases back to back.
 // Fused multi-head attention forward for sm_100a:  O = softmax(Q K^T * scale + mask) V  per (batch, head, 128-query tile)
 // with <= 256 keys and head_dim <= 192 — the shapes of the LayoutDETR path: BERT text encoder / decoder (T = 256,
 // head_dim 192, additive -10000 key mask, causal for the decoder; training/med.py:146-228) and DETR self / cross
@@ -313,13 +314,10 @@ int make_map(CUtensorMap* tm, const void* ptr, int64_t ld_, int d, int L, int H,
 }  // namespace
 
 // q / k / v point at column 0 of head 0 inside row-major [B*L, ld] bf16 buffers (head h at columns h*d .. h*d+d).
-extern "C" int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+extern "C" int ld_attention_fwd_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                 void* o, int64_t ldo, void* p_out, int64_t ldp, int B, int H, int Lq, int Lk, int d,
                                 float scale, const uint8_t* key_mask, int mask_inf, int causal, void* stream) {
     using namespace ld;
-    // opt-in two-CTAs-per-SM variant (attention2_sm100.cu); off unless LD_ATTN_V2=1 — it has not run on a B200 yet
-    static const int env_v2 = [] { const char* e = getenv("LD_ATTN_V2"); return e ? atoi(e) : 0; }();
-    if (env_v2) return ld_attention_fwd_v2(q, ldq, k, ldk, v, ldv, o, ldo, p_out, ldp, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal, stream);
     LD_CHECK_ARG(q && k && v && o && B > 0 && H > 0 && Lq > 0 && Lk > 0, "attention_fwd: bad argument");
     LD_CHECK_ARG(Lk <= 256 && d <= 192 && d % 8 == 0, "attention_fwd: needs <= 256 keys and head_dim <= 192 (multiple of 8); got Lk=%d d=%d", Lk, d);
     LD_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)o & 15) == 0 && (!p_out || (ldp % 8 == 0 && ((uintptr_t)p_out & 15) == 0)),

@@ -173,6 +173,58 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
         : "memory");
 }
 
+// TMA store of one rank-4 box from (swizzled) shared memory; rows / columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based dropout randomness: Philox4x32-10 (Salmon et al., the generator torch / cuRAND use for nn.Dropout —
+// reference training/med.py:96,213,240,318, training/detr_transformer.py:185-194,210).  One call yields 128 bits = eight
+// 16-bit lanes; element e of a group is dropped when lane e < thresh16 (thresh16 = round(p * 65536)).  The counter is
+// (group index lo, hi, site, step) and the key the 64-bit seed, so forward and backward kernels regenerate the same mask
+// from the element coordinates alone.  rng_state (device): {seed_lo, seed_hi, step, 0}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+struct DropoutRng {
+    uint2 key; uint32_t step, site, thresh16; float scale;          // thresh16 == 0: dropout off
+    __device__ __forceinline__ void init(const uint32_t* rng_state, uint32_t site_, uint32_t thresh16_, float scale_) {
+        site = site_; thresh16 = thresh16_; scale = scale_;
+        if (thresh16_) { key = make_uint2(__ldg(rng_state), __ldg(rng_state + 1)); step = __ldg(rng_state + 2); }
+        else { key = make_uint2(0u, 0u); step = 0u; }
+    }
+    // keep bits (bit e set = element e of the group survives) of the 8-element group `g`
+    __device__ __forceinline__ uint32_t keep8(uint64_t g) const {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), site, step), key);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m |= (((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu) >= thresh16 ? 1u : 0u) << e;
+        return m;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------

@@ -92,14 +92,22 @@ layernorm_fwd_kernel(const TIn* __restrict__ x, long ldx, const __nv_bfloat16* _
 // bf16 in (+ bf16 residual) -> bf16 out with 128-bit accesses: C % 256 == 0, one warp per row, eight columns per lane and
 // chunk.  (The generic kernel moves 8 bytes per lane and load; at [36864, 768] it reached 4.1 TB/s.)
 constexpr int LN8_MAX_CHUNKS = 4;     // 4 * 256 = 1024 columns
+// DROP: y = LayerNorm(dropout(x) + res) — hidden-state dropout of the post-norm residual blocks (BertSelfOutput / BertOutput
+// training/med.py:237-242,318-325; DETR dropout1/2/3 training/detr_transformer.py:210-214,270-285) applied where the dense
+// output is read anyway.  A lane's eight columns are one Philox group (index row * C/8 + column/8, the element order ld_dropout
+// uses on the contiguous [rows, C] gradient in the backward pass).  pre32 (optional) receives dropout(x) + res for LayerNorm's backward.
+struct LnDrop { const uint32_t* rng; uint32_t site, thresh16; float scale; float* pre32; long ldpre; };
+template <bool DROP>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const __nv_bfloat16* __restrict__ res, long ldr,
                           const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long ldy,
-                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int C, float eps) {
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int C, float eps, const LnDrop dp) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * LN_WARPS + warp;
     if (row >= rows) return;
     const int chunks = C >> 8;
+    DropoutRng rng;
+    rng.init(dp.rng, dp.site, DROP ? dp.thresh16 : 0u, dp.scale);
     float v[LN8_MAX_CHUNKS][8];
     uint4 xa[LN8_MAX_CHUNKS], ra[LN8_MAX_CHUNKS];
 #pragma unroll
@@ -116,10 +124,20 @@ layernorm_fwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, long ldx, const _
             const uint32_t w[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) unpack_bf16x2(w[k], v[j][2 * k], v[j][2 * k + 1]);
+            if (DROP) {
+                const uint32_t keep = rng.keep8((uint64_t)row * (uint64_t)(C >> 3) + (uint64_t)(j * 32 + lane));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j][k] = ((keep >> k) & 1u) ? v[j][k] * rng.scale : 0.0f;
+            }
             if (res) {
                 const uint32_t rw[4] = {ra[j].x, ra[j].y, ra[j].z, ra[j].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { float lo, hi; unpack_bf16x2(rw[k], lo, hi); v[j][2 * k] += lo; v[j][2 * k + 1] += hi; }
+            }
+            if (dp.pre32) {
+                float* pr = dp.pre32 + row * dp.ldpre + (j * 32 + lane) * 8;
+                *reinterpret_cast<float4*>(pr) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                *reinterpret_cast<float4*>(pr + 4) = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) s += v[j][k];
@@ -322,8 +340,8 @@ int ld_layernorm_res_fwd(const void* x, int x_dtype, int64_t ldx, const void* re
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (x_dtype == LD_BF16 && y_bf16 && !y_f32 && C % 256 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!res || ldr % 8 == 0) &&
         al16(x) && al16(y_bf16) && (!res || al16(res)) && al16(gamma) && al16(beta)) {
-        layernorm_fwd_vec8_kernel<<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, res, ldr, gamma, beta,
-                                                                   (__nv_bfloat16*)y_bf16, ldy, mean, rstd, rows, C, eps);
+        layernorm_fwd_vec8_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, res, ldr, gamma, beta,
+                                                                          (__nv_bfloat16*)y_bf16, ldy, mean, rstd, rows, C, eps, LnDrop{});
         ld::count_launch();
         LD_LAUNCH_CHECK("layernorm_fwd");
         return 0;
@@ -334,6 +352,35 @@ int ld_layernorm_res_fwd(const void* x, int x_dtype, int64_t ldx, const void* re
         layernorm_fwd_kernel<__nv_bfloat16><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, res, ldr, gamma, beta, (__nv_bfloat16*)y_bf16, y_f32, ldy, mean, rstd, rows, C, eps);
     ld::count_launch();
     LD_LAUNCH_CHECK("layernorm_fwd");
+    return 0;
+}
+
+int ld_layernorm_res_dropout_fwd(const void* x_bf16, int64_t ldx, const void* res_bf16, int64_t ldr,
+                                 const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* pre_f32, int64_t ldpre,
+                                 float* mean, float* rstd, int rows, int C, float eps,
+                                 float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream) {
+    int e = check_ln(rows, C); if (e) return e;
+    LD_CHECK_ARG(x_bf16 && gamma && beta && y_bf16, "layernorm_res_dropout_fwd: null pointer");
+    LD_CHECK_ARG(dropout_p >= 0.0f && dropout_p < 1.0f && (dropout_p == 0.0f || rng_state), "layernorm_res_dropout_fwd: dropout arguments");
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    LD_CHECK_ARG(C % 256 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (!res_bf16 || ldr % 8 == 0) && al16(x_bf16) && al16(y_bf16) &&
+                 (!res_bf16 || al16(res_bf16)) && al16(gamma) && al16(beta) && (!pre_f32 || (al16(pre_f32) && ldpre % 4 == 0)),
+                 "layernorm_res_dropout_fwd: needs C %% 256 == 0 and 16-byte aligned rows");
+    LnDrop dp{};
+    dp.rng = rng_state; dp.site = rng_site;
+    dp.thresh16 = dropout_p > 0.0f ? (uint32_t)(dropout_p * 65536.0f + 0.5f) : 0u;
+    dp.scale = dropout_p > 0.0f ? 65536.0f / (65536.0f - (float)dp.thresh16) : 1.0f;
+    dp.pre32 = pre_f32; dp.ldpre = ldpre;
+    const int grid = ld::ceil_div(rows, LN_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dp.thresh16)
+        layernorm_fwd_vec8_kernel<true><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x_bf16, ldx, (const __nv_bfloat16*)res_bf16, ldr,
+                                                                         gamma, beta, (__nv_bfloat16*)y_bf16, ldy, mean, rstd, rows, C, eps, dp);
+    else
+        layernorm_fwd_vec8_kernel<false><<<grid, LN_WARPS * 32, 0, st>>>((const __nv_bfloat16*)x_bf16, ldx, (const __nv_bfloat16*)res_bf16, ldr,
+                                                                          gamma, beta, (__nv_bfloat16*)y_bf16, ldy, mean, rstd, rows, C, eps, dp);
+    ld::count_launch();
+    LD_LAUNCH_CHECK("layernorm_res_dropout_fwd");
     return 0;
 }
 

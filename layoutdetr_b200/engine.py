@@ -11,10 +11,15 @@ import torch
 
 from . import kernels as K
 
-_shadow = {}          # (id(param), tag) -> (version, data_ptr, generation, tensor, params, make_fn)
-_managed = {}         # id(param) -> bf16 [N, K] view kept fresh by the fused optimizer kernel (flat storage)
+_shadow = {}          # (id(param)..., tag) -> (versions, data_ptrs, generations, tensor, weakrefs of the params, make_fn(*params))
+_managed = {}         # id(param) -> [weakref(param), data_ptr, version, bf16 [N, K] view kept fresh by the fused optimizer kernel]
 _generation = {}      # id(param) -> int, bumped when a kernel rewrites the parameter through a raw pointer
 _SM_COUNT = None
+
+# Ownership rules (a long run deep-copies G_ema for every snapshot / evaluation sweep and drops the copies again):
+#   * nothing in these tables holds a strong reference to a parameter — make functions receive the live tensors as arguments;
+#   * an entry is only ever returned for the very object it was built from (`weakref() is param`, so a recycled id() cannot hit);
+#   * entries die with their parameters (weakref.finalize), taking the bf16 shadows with them.
 
 
 def sm_count():
@@ -30,10 +35,32 @@ def clear_cache():
     _generation.clear()
 
 
+def _evict(key):
+    _shadow.pop(key, None)
+
+
+def _forget_param(pid):
+    _managed.pop(pid, None)
+    _generation.pop(pid, None)
+
+
 def register_managed(param, shadow):
     """`shadow` (bf16 [N, K] view of the flat bf16 buffer) is rewritten together with `param` by ld_adam_flat /
-    ld_ema_flat, so it is always current."""
-    _managed[id(param)] = (param.data_ptr(), shadow)
+    ld_ema_flat.  A torch-level in-place write to the parameter (load_state_dict, copy_params_and_buffers, a broadcast from
+    rank 0) bumps its version counter instead; w_bf16 / refresh_stale then re-cast the shadow before anything reads it."""
+    _managed[id(param)] = [weakref.ref(param), param.data_ptr(), param._version, shadow]
+    weakref.finalize(param, _forget_param, id(param))
+
+
+def _managed_shadow(param):
+    man = _managed.get(id(param))
+    if man is None or man[0]() is not param or man[1] != param.data_ptr():
+        return None
+    if man[2] != param._version:                       # written behind the optimizer kernel's back: re-cast in place
+        with torch.no_grad():
+            man[3].copy_(param.detach().reshape(man[3].shape))
+        man[2] = param._version
+    return man[3]
 
 
 def bump_generation(params):
@@ -42,14 +69,19 @@ def bump_generation(params):
         _generation[id(p)] = _generation.get(id(p), 0) + 1
 
 
+def _stamp(params):
+    return (tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
+            tuple(_generation.get(id(p), 0) for p in params))
+
+
 def _lookup(key, params):
     ent = _shadow.get(key)
     if ent is None:
         return None
-    ver = tuple(p._version for p in params)
-    ptr = tuple(p.data_ptr() for p in params)
-    gen = tuple(_generation.get(id(p), 0) for p in params)
-    if ent[0] == ver and ent[1] == ptr and ent[2] == gen:
+    if any(r() is not p for r, p in zip(ent[4], params)):       # same id(), different object: a stale entry of a dead module
+        del _shadow[key]
+        return None
+    if (ent[0], ent[1], ent[2]) == _stamp(params):
         return ent[3]
     return None
 
@@ -64,8 +96,11 @@ def _store(key, params, value, fn=None):
         value = old[3]
     if fn is None and old is not None:
         fn = old[5]
-    _shadow[key] = (tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
-                    tuple(_generation.get(id(p), 0) for p in params), value, tuple(weakref.ref(p) for p in params), fn)
+    if old is None:
+        for p in params:
+            weakref.finalize(p, _evict, key)
+    ver, ptr, gen = _stamp(params)
+    _shadow[key] = (ver, ptr, gen, value, tuple(weakref.ref(p) for p in params), fn)
     return value
 
 
@@ -74,6 +109,14 @@ def refresh_stale(only_ids=None):
     The lane scheduler (lanes.py) calls this before it forks: a shadow refreshed lazily inside one lane would race with
     readers in another lane.  Plain weight shadows first — concatenations are built from them.  `only_ids`: restrict to
     shadows derived from parameters / buffers with these `id()`s (the modules the caller is about to run)."""
+    n = 0
+    for pid, man in list(_managed.items()):
+        p = man[0]()
+        if p is None:
+            _managed.pop(pid, None)
+        elif (only_ids is None or pid in only_ids) and man[2] != p._version:
+            _managed_shadow(p)
+            n += 1
     stale = []
     for key, ent in list(_shadow.items()):
         params = tuple(r() for r in ent[4])
@@ -82,70 +125,80 @@ def refresh_stale(only_ids=None):
             continue
         if ent[5] is None or (only_ids is not None and not all(id(p) in only_ids for p in params)):
             continue
-        if ent[0] != tuple(p._version for p in params) or ent[1] != tuple(p.data_ptr() for p in params) or \
-                ent[2] != tuple(_generation.get(id(p), 0) for p in params):
+        if (ent[0], ent[1], ent[2]) != _stamp(params):
             stale.append((0 if key[1] == "w" else 1, key, params, ent[5]))
     stale.sort(key=lambda t: t[0])
     for _, key, params, fn in stale:
         with torch.no_grad():
-            v = fn()
+            v = fn(*params)
         _store(key, params, v, fn)
-    return len(stale)
+    return n + len(stale)
 
 
 def pad8(n):
     return (n + 7) // 8 * 8
 
 
+def _make_w(param):
+    w = param.detach()
+    w2 = w.reshape(w.shape[0], -1)
+    return K.cast_pad(w2, torch.bfloat16, pad8(w2.shape[1]))
+
+
 def w_bf16(param):
     """bf16 shadow of a 2-D weight [N, K] with K zero-padded to a multiple of 8 (TMA stride rule)."""
-    man = _managed.get(id(param))
-    if man is not None and man[0] == param.data_ptr():
-        return man[1]
+    man = _managed_shadow(param)
+    if man is not None:
+        return man
     key = (id(param), "w")
     v = _lookup(key, (param,))
     if v is None:
-        def make():
-            w = param.detach()
-            w2 = w.reshape(w.shape[0], -1)
-            return K.cast_pad(w2, torch.bfloat16, pad8(w2.shape[1]))
         with torch.no_grad():
-            v = make()
-        v = _store(key, (param,), v, make)
+            v = _make_w(param)
+        v = _store(key, (param,), v, _make_w)
     return v
+
+
+def _make_wcat(*params):
+    return torch.cat([w_bf16(p) for p in params], dim=0)
+
+
+def _make_bcat(*params):
+    return torch.cat([p.detach().float() for p in params], dim=0).contiguous()
 
 
 def w_cat_bf16(params):
     """bf16 shadow of several [Ni, K] weights concatenated along N (fused QKV projections)."""
+    params = tuple(params)
     key = (tuple(id(p) for p in params), "cat")
     v = _lookup(key, params)
     if v is None:
-        make = lambda: torch.cat([w_bf16(p) for p in params], dim=0)
         with torch.no_grad():
-            v = make()
-        v = _store(key, params, v, make)
+            v = _make_wcat(*params)
+        v = _store(key, params, v, _make_wcat)
     return v
 
 
 def b_cat_f32(params):
+    params = tuple(params)
     key = (tuple(id(p) for p in params), "bcat")
     v = _lookup(key, params)
     if v is None:
-        make = lambda: torch.cat([p.detach().float() for p in params], dim=0).contiguous()
         with torch.no_grad():
-            v = make()
-        v = _store(key, params, v, make)
+            v = _make_bcat(*params)
+        v = _store(key, params, v, _make_bcat)
     return v
 
 
 def derived(param_tuple, tag, fn):
-    """Cache an arbitrary tensor derived from parameters / buffers (e.g. folded FrozenBN scale+bias,
-    conv weights re-laid out as [Cout, kh*kw*Cin])."""
+    """Cache an arbitrary tensor derived from parameters / buffers (e.g. folded FrozenBN scale+bias, conv weights re-laid out
+    as [Cout, kh*kw*Cin]).  `fn(*param_tuple)` builds it and must not capture the tensors (it is kept for in-place refreshes)."""
+    param_tuple = tuple(param_tuple)
     key = (tuple(id(p) for p in param_tuple), tag)
     v = _lookup(key, param_tuple)
     if v is None:
         with torch.no_grad():
-            v = fn()
+            v = fn(*param_tuple)
         v = _store(key, param_tuple, v, fn)
     return v
 

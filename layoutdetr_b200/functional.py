@@ -14,6 +14,7 @@ import torch
 
 from . import engine as E
 from . import kernels as K
+from . import rng as RNG
 
 
 def _needs(p):
@@ -210,20 +211,35 @@ LN_BF16_DENSE_NOGRAD = _os.environ.get("LD_LN_BF16_DENSE", "1") != "0"   # see L
 
 
 class LinearLNFn(_Fn):
-    """y = LayerNorm(x @ W^T + b + residual) — the post-norm residual block tail (BERT SelfOutput /
+    """y = LayerNorm(dropout(x @ W^T + b) + residual) — the post-norm residual block tail (BERT SelfOutput /
     Output: training/med.py:237-242,321-325; DETR: training/detr_transformer.py:210-214).  The pre-norm
     sum is formed in fp32.  When the block needs no gradient (frozen text encoder, inference) and the residual is bf16,
     the dense output travels to the LayerNorm kernel as bf16 and the residual is added there (half the GEMM's store
     traffic, and its plain bf16 epilogue instead of the fp32 + residual one); with gradients the fp32 sum is kept
-    for the backward pass."""
+    for the backward pass.  With dropout (training mode) the dense output always takes the bf16 route: the mask is drawn
+    where the LayerNorm kernel reads it (ld_layernorm_res_dropout_fwd) and re-applied to the gradient in backward."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, ln_w, ln_b, eps):
+    def forward(ctx, x, residual, weight, bias, ln_w, ln_b, eps, dropout_p):
         w16 = E.w_bf16(weight)
         M, N = x.shape[0], weight.shape[0]
         need_grad = _need(ctx)
-        if (LN_BF16_DENSE_NOGRAD and not need_grad and residual is not None and residual.dtype == torch.bfloat16
-                and residual.stride(1) == 1 and M * N >= (1 << 20)):
+        ctx.drop = None
+        res_ok = residual is not None and residual.dtype == torch.bfloat16 and residual.stride(1) == 1
+        if dropout_p > 0.0:
+            if not (res_ok and N % 256 == 0):
+                raise RuntimeError("linear_ln: dropout needs a bf16 residual and N %% 256 == 0 (got N=%d)" % N)
+            dense = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+            K.linear(x, w16, bias.detach() if bias is not None else None, out=dense)
+            site = RNG.next_site()
+            y, pre, mean, rstd = K.layernorm_res_dropout_fwd(dense, residual, ln_w.detach(), ln_b.detach(), eps, dropout_p, site,
+                                                             save=need_grad)
+            ctx.weight, ctx.bias, ctx.ln_w, ctx.ln_b = weight, bias, ln_w, ln_b
+            ctx.drop = (dropout_p, site)
+            if need_grad:
+                ctx.save_for_backward(x, pre, mean, rstd)
+            return y
+        if LN_BF16_DENSE_NOGRAD and not need_grad and res_ok and M * N >= (1 << 20):
             dense = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
             K.linear(x, w16, bias.detach() if bias is not None else None, out=dense)
             y, _, _, _ = K.layernorm_fwd(dense, ln_w.detach(), ln_b.detach(), eps, residual=residual)
@@ -242,17 +258,37 @@ class LinearLNFn(_Fn):
         dgamma = E.grad_buffer(ctx.ln_w) if _needs(ctx.ln_w) else None
         dbeta = E.grad_buffer(ctx.ln_b) if _needs(ctx.ln_b) else None
         dpre = K.layernorm_bwd(dy.contiguous(), pre, mean, rstd, ctx.ln_w.detach(), dgamma, dbeta)
-        dx = _dgrad(dpre, E.w_bf16(ctx.weight), x.shape[1]) if ctx.needs_input_grad[0] else None
+        ddense = K.dropout(dpre, ctx.drop[0], ctx.drop[1]) if ctx.drop is not None else dpre     # same Philox mask as the forward
+        dx = _dgrad(ddense, E.w_bf16(ctx.weight), x.shape[1]) if ctx.needs_input_grad[0] else None
         if _needs(ctx.weight):
-            _wgrad(ctx.weight, 0, ctx.weight.shape[0], dpre, x)
+            _wgrad(ctx.weight, 0, ctx.weight.shape[0], ddense, x)
         if _needs(ctx.bias):
-            _bgrad(ctx.bias, 0, ctx.bias.shape[0], dpre)
+            _bgrad(ctx.bias, 0, ctx.bias.shape[0], ddense)
         dres = dpre if ctx.needs_input_grad[1] else None
-        return dx, dres, None, None, None, None, None
+        return dx, dres, None, None, None, None, None, None
 
 
-def linear_ln(x, residual, weight, bias, ln_w, ln_b, eps):
-    return LinearLNFn.apply(x, residual, weight, bias, ln_w, ln_b, eps)
+def linear_ln(x, residual, weight, bias, ln_w, ln_b, eps, dropout_p=0.0):
+    return LinearLNFn.apply(x, residual, weight, bias, ln_w, ln_b, eps, float(dropout_p))
+
+
+class DropoutFn(_Fn):
+    """y = dropout(x) on a contiguous bf16 / fp32 tensor (embedding dropout training/med.py:96, the FFN-inner dropout of
+    training/detr_transformer.py:212 and of nn.TransformerEncoderLayer); the backward pass re-applies the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, dropout_p):
+        site = RNG.next_site()
+        ctx.drop = (dropout_p, site)
+        return K.dropout(x.contiguous(), dropout_p, site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.dropout(dy.contiguous(), ctx.drop[0], ctx.drop[1]), None
+
+
+def dropout(x, dropout_p):
+    return DropoutFn.apply(x, float(dropout_p)) if dropout_p > 0.0 else x
 
 
 class LayerNormFn(_Fn):
@@ -325,34 +361,39 @@ FUSED_ATTENTION = True       # False -> batched-GEMM attention (QK^T with fused 
 
 
 class AttentionFn(_Fn):
-    """Multi-head attention core on projected buffers via batched tcgen05 GEMMs + masked softmax.
+    """Multi-head attention core on projected buffers.
 
-      S = (Q K^T) * scale (+ mask);  P = softmax(S);  O = P V        per (batch b, head h)
+      S = (Q K^T) * scale (+ mask);  P = softmax(S);  O = dropout(P) V        per (batch b, head h)
 
     q_t / k_t / v_t are 2-D bf16 buffers `[B*L, ld]`; head h of q lives in columns
     [q_off + h*d, q_off + (h+1)*d).  They may alias (fused QKV / QK buffers); gradients are returned
     once per distinct buffer.  Reference: BertSelfAttention.forward training/med.py:146-228 and
     F.multi_head_attention_forward as used by training/detr_transformer.py:208,273,277.
+
+    <= 256 keys, head_dim <= 192: one fused kernel forward (ld_attention_fwd; only a per-row log-sum-exp is saved) and one
+    fused kernel backward (ld_attention_bwd: P recomputed, dropout mask regenerated, dQ on chip) + the two transposed GEMMs.
+    Larger shapes: batched tcgen05 GEMMs with the softmax in the first GEMM's epilogue / a masked-softmax kernel.
     """
 
     @staticmethod
-    def forward(ctx, q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal):
+    def forward(ctx, q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal, dropout_p):
         dev = q_t.device
         Lkp = E.pad8(Lk)
         ldq, ldk, ldv = q_t.stride(0), k_t.stride(0), v_t.stride(0)
         need_grad = _need(ctx)
         ctx.dims = (q_off, k_off, v_off, B, H, Lq, Lk, d, scale)
-        if Lk <= 256 and d <= 192 and d % 8 == 0 and FUSED_ATTENTION:
-            # one kernel: QK^T -> mask/softmax -> PV; probabilities only go to HBM when the backward pass needs them
-            P = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev) if need_grad else None
-            if P is not None and Lkp != Lk:
-                P.zero_()
+        ctx.mask = (key_mask, mask_inf, causal)
+        site = RNG.next_site() if dropout_p > 0.0 else 0
+        ctx.drop = (dropout_p, site)
+        ctx.fused = bool(Lk <= 256 and d <= 192 and d % 8 == 0 and FUSED_ATTENTION)
+        if ctx.fused:
+            lse = torch.empty((B * H, Lq), dtype=torch.float32, device=dev) if need_grad else None
             O = K.attention_fwd(q_t, q_off, k_t, k_off, v_t, v_off, B, H, Lq, Lk, d, scale, key_mask=key_mask,
-                                mask_inf=mask_inf, causal=causal, P_out=P)
+                                mask_inf=mask_inf, causal=causal, lse_out=lse, dropout_p=dropout_p, rng_site=site)
             if need_grad:
-                ctx.save_for_backward(q_t, k_t, v_t, P)
+                ctx.save_for_backward(q_t, k_t, v_t, O, lse)
             return O
-        P = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
+        P = (torch.zeros if Lkp != Lk else torch.empty)((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
         if Lk <= 256:
             # scores never leave the SM: scale + mask + softmax + bf16 cast run in the GEMM's TMEM drain
             K.gemm(Lq, Lk, d, K.Op(q_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d),
@@ -364,29 +405,24 @@ class AttentionFn(_Fn):
                    K.Out(S, Lk, sb1=H * Lq * Lk, sb2=Lq * Lk), nb1=B, nb2=H)
             K.softmax_fwd(S, P, B, H, Lq, Lk, scale, key_mask=key_mask, mask_inf=mask_inf, causal=causal)
             del S
+        Pd = K.dropout(P, dropout_p, site) if dropout_p > 0.0 else P
         O = torch.empty((B * Lq, H * d), dtype=torch.bfloat16, device=dev)
-        K.gemm(Lq, d, Lk, K.Op(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d, mn=True),
+        K.gemm(Lq, d, Lk, K.Op(Pd, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d, mn=True),
                K.Out(O, H * d, sb1=Lq * H * d, sb2=d), nb1=B, nb2=H)
-        ctx.dims = (q_off, k_off, v_off, B, H, Lq, Lk, d, scale)
-        if _need(ctx):
-            ctx.save_for_backward(q_t, k_t, v_t, P)
+        if need_grad:
+            ctx.save_for_backward(q_t, k_t, v_t, P, Pd)
         return O
 
     @staticmethod
     def backward(ctx, dO):
-        q_t, k_t, v_t, P = ctx.saved_tensors
         q_off, k_off, v_off, B, H, Lq, Lk, d, scale = ctx.dims
+        key_mask, mask_inf, causal = ctx.mask
+        dropout_p, site = ctx.drop
         dev = dO.device
         dO = dO.contiguous()
-        Lkp = P.shape[2]
+        Lkp = E.pad8(Lk)
+        q_t, k_t, v_t = ctx.saved_tensors[:3]
         ldq, ldk, ldv, ldo = q_t.stride(0), k_t.stride(0), v_t.stride(0), H * d
-        # dP = dO V^T
-        dP = torch.empty((B * H, Lq, Lk), dtype=torch.float32, device=dev)
-        K.gemm(Lq, Lk, d, K.Op(dO, ldo, sb1=Lq * ldo, sb2=d), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d),
-               K.Out(dP, Lk, sb1=H * Lq * Lk, sb2=Lq * Lk), nb1=B, nb2=H)
-        dS = torch.empty_like(P) if Lkp == Lk else torch.zeros_like(P)
-        K.softmax_bwd(P, dP, dS, B * H, Lq, Lk, scale)
-        del dP
         # gradient buffers, one per distinct input buffer
         bufs = {}
         ptrs = [q_t.data_ptr(), k_t.data_ptr(), v_t.data_ptr()]
@@ -400,24 +436,43 @@ class AttentionFn(_Fn):
             return bufs[key]
 
         dq_t, dk_t, dv_t = gbuf(q_t), gbuf(k_t), gbuf(v_t)
-        # dQ = dS K
-        K.gemm(Lq, d, Lk, K.Op(dS, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d, mn=True),
-               K.Out(dq_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), nb1=B, nb2=H)
+        if ctx.fused:
+            O, lse = ctx.saved_tensors[3:]
+            Pd = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
+            dS = torch.empty((B * H, Lq, Lkp), dtype=torch.bfloat16, device=dev)
+            # P recomputed from lse, dropout mask regenerated, dQ = dS K — all in one kernel
+            K.attention_bwd(q_t, q_off, k_t, k_off, v_t, v_off, O, dO, lse, dq_t, Pd, dS, B, H, Lq, Lk, d, scale,
+                            key_mask=key_mask, mask_inf=mask_inf, causal=causal, dropout_p=dropout_p, rng_site=site)
+        else:
+            P, Pd = ctx.saved_tensors[3:]
+            # dP = dO V^T  (gradient w.r.t. the dropped probabilities)
+            dP = (torch.zeros if Lkp != Lk else torch.empty)((B * H, Lq, Lkp), dtype=torch.float32, device=dev)
+            K.gemm(Lq, Lk, d, K.Op(dO, ldo, sb1=Lq * ldo, sb2=d), K.Op(v_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d),
+                   K.Out(dP, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), nb1=B, nb2=H)
+            if dropout_p > 0.0:
+                K.dropout(dP, dropout_p, site, out=dP)
+            dS = torch.empty_like(P) if Lkp == Lk else torch.zeros_like(P)
+            K.softmax_bwd(P, dP, dS, B * H, Lq, Lk, scale)
+            del dP
+            # dQ = dS K
+            K.gemm(Lq, d, Lk, K.Op(dS, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp), K.Op(k_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d, mn=True),
+                   K.Out(dq_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d), nb1=B, nb2=H)
         # dK = dS^T Q
         K.gemm(Lk, d, Lq, K.Op(dS, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp, mn=True), K.Op(q_t, ldq, off=q_off, sb1=Lq * ldq, sb2=d, mn=True),
                K.Out(dk_t, ldk, off=k_off, sb1=Lk * ldk, sb2=d), nb1=B, nb2=H)
-        # dV = P^T dO
-        K.gemm(Lk, d, Lq, K.Op(P, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp, mn=True), K.Op(dO, ldo, sb1=Lq * ldo, sb2=d, mn=True),
+        # dV = dropout(P)^T dO
+        K.gemm(Lk, d, Lq, K.Op(Pd, Lkp, sb1=H * Lq * Lkp, sb2=Lq * Lkp, mn=True), K.Op(dO, ldo, sb1=Lq * ldo, sb2=d, mn=True),
                K.Out(dv_t, ldv, off=v_off, sb1=Lk * ldv, sb2=d), nb1=B, nb2=H)
         gq = dq_t
         gk = dk_t if k_t.data_ptr() != q_t.data_ptr() else None
         gv = dv_t if v_t.data_ptr() not in (q_t.data_ptr(), k_t.data_ptr()) else None
-        return (gq, gk, gv) + (None,) * 12
+        return (gq, gk, gv) + (None,) * 13
 
 
-def attention(q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale=None, key_mask=None, mask_inf=False, causal=False):
+def attention(q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale=None, key_mask=None, mask_inf=False, causal=False,
+              dropout_p=0.0):
     scale = (1.0 / math.sqrt(d)) if scale is None else scale
-    return AttentionFn.apply(q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal)
+    return AttentionFn.apply(q_t, k_t, v_t, q_off, k_off, v_off, B, H, Lq, Lk, d, scale, key_mask, mask_inf, causal, float(dropout_p))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -496,13 +551,15 @@ def cross_entropy(logits, labels):
 
 # ------------------------------------------------------------------------------------------------
 # convolution = (im2col) + tcgen05 GEMM with fused per-channel scale/bias (+residual) (+ReLU)
+def _make_ohwi(weight):
+    Cout = weight.shape[0]
+    w = weight.detach().permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    return K.cast_pad(w, torch.bfloat16, E.pad8(w.shape[1]))
+
+
 def conv_weight_bf16(weight):
     """OIHW fp32 parameter -> bf16 [Cout, pad8(KH*KW*Cin)] with K ordered (kh, kw, ci) to match im2col."""
-    def make():
-        Cout = weight.shape[0]
-        w = weight.detach().permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
-        return K.cast_pad(w, torch.bfloat16, E.pad8(w.shape[1]))
-    return E.derived((weight,), "ohwi", make)
+    return E.derived((weight,), "ohwi", _make_ohwi)
 
 
 class Conv2dFn(_Fn):
@@ -648,7 +705,7 @@ class ScaledLinearFn(_Fn):
         w16 = E.w_bf16(weight)
         b = None
         if bias is not None:
-            b = E.derived((bias,), "bg%g" % bg, lambda: (bias.detach().float() * bg).contiguous())
+            b = E.derived((bias,), "bg%g" % bg, lambda t, g=float(bg): (t.detach().float() * g).contiguous())
         out = torch.empty((x.shape[0], weight.shape[0]), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
         K.linear(x, w16, b, act=act, out=out, alpha=wg, post_gain=gain)
         ctx.cfg = (wg, bg, act, gain, out_f32)
@@ -754,12 +811,14 @@ class ConvTransposeUp2Fn(_Fn):
     GEMM  cols = x @ Wt^T  ([B*H*W, 9*Cout], tcgen05)  followed by the gather-form col2im."""
 
     @staticmethod
+    def _make_khkwoi(weight):
+        Cout, Cin, KH, KW = weight.shape
+        w = weight.detach().permute(2, 3, 0, 1).reshape(KH * KW * Cout, Cin).contiguous()
+        return K.cast_pad(w, torch.bfloat16, E.pad8(Cin))
+
+    @staticmethod
     def wt(weight):
-        def make():
-            Cout, Cin, KH, KW = weight.shape
-            w = weight.detach().permute(2, 3, 0, 1).reshape(KH * KW * Cout, Cin).contiguous()
-            return K.cast_pad(w, torch.bfloat16, E.pad8(Cin))
-        return E.derived((weight,), "khkwoi", make)
+        return E.derived((weight,), "khkwoi", ConvTransposeUp2Fn._make_khkwoi)
 
     @staticmethod
     def forward(ctx, x, weight, B, H, W):

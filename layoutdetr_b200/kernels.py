@@ -205,19 +205,73 @@ def embed_bwd(ids, dpre, dword, dpos, T, pad_id):
                              _stream()), "ld_embed_bwd")
 
 
+def _rng_ptr(dropout_p, device):
+    if dropout_p <= 0.0:
+        return c_void_p(0)
+    from . import rng
+    return c_void_p(rng.state(device).data_ptr())
+
+
 def attention_fwd(q_t, q_off, k_t, k_off, v_t, v_off, B, H, Lq, Lk, d, scale, key_mask=None, mask_inf=False, causal=False,
-                  P_out=None):
+                  P_out=None, lse_out=None, dropout_p=0.0, rng_site=0):
     """Fused attention forward. q_t/k_t/v_t: bf16 [B*L, ld] buffers (may alias), head h of q at columns q_off + h*d.
-    Returns O bf16 [B*Lq, H*d]; fills P_out [B*H, Lq, pad8(Lk)] with the probabilities if given."""
+    Returns O bf16 [B*Lq, H*d]; fills lse_out [B*H, Lq] (log2-domain log-sum-exp, for attention_bwd) and / or the legacy
+    P_out [B*H, Lq, pad8(Lk)] with the probabilities if given."""
     _cuda(q_t, k_t, v_t)
     O = torch.empty((B * Lq, H * d), dtype=torch.bfloat16, device=q_t.device)
     check(lib().ld_attention_fwd(c_void_p(q_t.data_ptr() + 2 * q_off), c_int64(q_t.stride(0)),
                                  c_void_p(k_t.data_ptr() + 2 * k_off), c_int64(k_t.stride(0)),
                                  c_void_p(v_t.data_ptr() + 2 * v_off), c_int64(v_t.stride(0)),
-                                 _p(O), c_int64(H * d), _p(P_out), c_int64(P_out.stride(1) if P_out is not None else 0),
+                                 _p(O), c_int64(H * d), _p(P_out), c_int64(P_out.stride(1) if P_out is not None else 0), _p(lse_out),
                                  c_int(B), c_int(H), c_int(Lq), c_int(Lk), c_int(d), c_float(scale), _p(key_mask),
-                                 c_int(1 if mask_inf else 0), c_int(1 if causal else 0), _stream()), "ld_attention_fwd")
+                                 c_int(1 if mask_inf else 0), c_int(1 if causal else 0), c_float(dropout_p),
+                                 _rng_ptr(dropout_p, q_t.device), ctypes.c_uint32(rng_site), _stream()), "ld_attention_fwd")
     return O
+
+
+def attention_bwd(q_t, q_off, k_t, k_off, v_t, v_off, O, dO, lse, dq_t, Pd, dS, B, H, Lq, Lk, d, scale, key_mask=None,
+                  mask_inf=False, causal=False, dropout_p=0.0, rng_site=0):
+    """Fused attention backward: writes dQ into dq_t (same layout / offset as q_t), dropout(P) into Pd and dS into dS
+    (both bf16 [B*H, Lq, pad8(Lk)]) for the transposed dV / dK products."""
+    _cuda(q_t, k_t, v_t, O, dO, lse, dq_t, Pd, dS)
+    assert O.stride(0) == dO.stride(0) and Pd.stride(1) == dS.stride(1) and Pd.is_contiguous() and dS.is_contiguous()
+    check(lib().ld_attention_bwd(c_void_p(q_t.data_ptr() + 2 * q_off), c_int64(q_t.stride(0)),
+                                 c_void_p(k_t.data_ptr() + 2 * k_off), c_int64(k_t.stride(0)),
+                                 c_void_p(v_t.data_ptr() + 2 * v_off), c_int64(v_t.stride(0)),
+                                 _p(O), _p(dO), c_int64(O.stride(0)), _p(lse),
+                                 c_void_p(dq_t.data_ptr() + 2 * q_off), c_int64(dq_t.stride(0)), _p(Pd), _p(dS), c_int64(Pd.stride(1)),
+                                 c_int(B), c_int(H), c_int(Lq), c_int(Lk), c_int(d), c_float(scale), _p(key_mask),
+                                 c_int(1 if mask_inf else 0), c_int(1 if causal else 0), c_float(dropout_p),
+                                 _rng_ptr(dropout_p, q_t.device), ctypes.c_uint32(rng_site), _stream()), "ld_attention_bwd")
+
+
+def dropout(x, dropout_p, rng_site, out=None):
+    """y = keep ? x / (1 - p) : 0 with the Philox mask of `rng_site` (contiguous bf16 / fp32, numel % 8 == 0)."""
+    _cuda(x)
+    assert x.is_contiguous() and x.numel() % 8 == 0
+    y = torch.empty_like(x) if out is None else out
+    check(lib().ld_dropout(_p(x), _p(y), c_int(dt(x)), c_int64(x.numel()), c_float(dropout_p), _rng_ptr(dropout_p, x.device),
+                           ctypes.c_uint32(rng_site), _stream()), "ld_dropout")
+    return y
+
+
+def layernorm_res_dropout_fwd(x, residual, gamma, beta, eps, dropout_p, rng_site, save=False):
+    """y = LayerNorm(dropout(x) + residual) (bf16 in / out); with `save` also returns dropout(x) + residual (fp32), mean, rstd."""
+    _cuda(x, gamma, beta)
+    rows, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == x.shape and residual.stride(1) == 1
+    y = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device)
+    pre = torch.empty((rows, C), dtype=torch.float32, device=x.device) if save else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save else None
+    check(lib().ld_layernorm_res_dropout_fwd(_p(x), c_int64(x.stride(0)), _p(residual),
+                                             c_int64(residual.stride(0) if residual is not None else 0), _p(gamma), _p(beta),
+                                             _p(y), c_int64(C), _p(pre), c_int64(C), _p(mean), _p(rstd), c_int(rows), c_int(C),
+                                             c_float(eps), c_float(dropout_p), _rng_ptr(dropout_p, x.device),
+                                             ctypes.c_uint32(rng_site), _stream()), "ld_layernorm_res_dropout_fwd")
+    return y, pre, mean, rstd
 
 
 def softmax_fwd(S, P, nb1, nb2, rows, cols, scale, key_mask=None, mask_inf=False, causal=False):

@@ -1,6 +1,7 @@
-"""Box losses of the LayoutDETR training objective (mirror of the functions training/loss.py imports from the
-reference's metrics/metric_layoutnet.py: generalized_iou_loss :245-275, compute_overlap :153-179,
-compute_alignment :182-201) and the Hungarian max-IoU helpers (:100-126) on the lsap kernel.
+"""Box losses of the LayoutDETR training objective: mirror of the functions training/loss.py imports from the
+reference's metrics/metric_layoutnet.py (generalized_iou_loss :245-275, compute_overlap :153-179,
+compute_alignment :182-201) plus `compute_maximum_iou` (:100-150, the Hungarian max-IoU metric — dead code in the
+reference, served here by the batched ld_lsap kernel).
 
 The three losses act on `[B, 9, 4]` boxes: negligible FLOPs, so they are evaluated by fused CUDA kernels
 (csrc/box_loss.cu: value + analytic Jacobian in one launch, backward = one scaling launch) instead of ~60 eager launches.

@@ -13,7 +13,27 @@ import torch
 
 from . import eval_sweep
 
-_cache = {}          # (id(G), dataset path, max_real, rank) -> metric dict of the last sweep
+import weakref
+
+# Result of the last sweep, shared by the two metric entry points metric_main calls back to back on the SAME snapshot.
+# Scoped to one generator OBJECT (weak reference, so a recycled id() of a later snapshot can never hit) and to a fingerprint of
+# its weights; with several ranks the hit / miss decision is made collectively, so no rank can skip a sweep (and its
+# all-reduce) that another rank enters.
+_cache = {"ref": None, "key": None, "res": None}
+
+
+def _fingerprint(G):
+    """Cheap content stamp of a module: version counters + storage addresses of its parameters / buffers."""
+    return tuple((t.data_ptr(), t._version) for t in list(G.parameters()) + list(G.buffers()))
+
+
+def _cache_lookup(opts, key):
+    hit = (_cache["ref"] is not None and _cache["ref"]() is opts.G and _cache["key"] == key)
+    if getattr(opts, "num_gpus", 1) > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+        flag = torch.tensor([1 if hit else 0], dtype=torch.int32, device=opts.device)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)       # a hit only if EVERY rank hits
+        hit = bool(int(flag.item()))
+    return _cache["res"] if hit else None
 
 
 def rank_item_subset(num_items, num_gpus, rank):
@@ -40,9 +60,10 @@ def sweep(opts, max_real=None, batch_size=64, num_workers=3):
     """One evaluation sweep for `opts` (the reference's MetricOptions: G, dataset_kwargs, num_gpus, rank, device, G_kwargs)."""
     from ..training import dataset_layoutganpp as dl
     path = opts.dataset_kwargs["path"]
-    key = (id(opts.G), path, max_real, opts.rank)
-    if key in _cache:
-        return _cache[key]
+    key = (_fingerprint(opts.G), path, max_real, opts.rank, opts.num_gpus)
+    cached = _cache_lookup(opts, key)
+    if cached is not None:
+        return cached
     kw = {k: v for k, v in dict(opts.dataset_kwargs).items() if k != "class_name"}
     dataset = dl.LayoutDataset(**dict(kw, lean=True))
     num_items = len(dataset) if max_real is None else min(len(dataset), max_real)
@@ -54,8 +75,7 @@ def sweep(opts, max_real=None, batch_size=64, num_workers=3):
     batches = (dl.to_device(b, opts.device) for b in loader)
     res = eval_sweep.run_sweep(G, net, batches, z_seed=opts.rank, label_idx_replace=rep, label_idx_replace_2=rep2,
                                G_kwargs=dict(getattr(opts, "G_kwargs", {}) or {}))
-    _cache.clear()
-    _cache[key] = res
+    _cache.update(ref=weakref.ref(opts.G), key=key, res=res)
     return res
 
 

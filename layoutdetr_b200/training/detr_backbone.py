@@ -29,14 +29,14 @@ class FrozenBatchNorm2d(nn.Module):
         state_dict.pop(prefix + "num_batches_tracked", None)
         super()._load_from_state_dict(state_dict, prefix, *args)
 
-    def folded(self):
-        bufs = (self.weight, self.bias, self.running_mean, self.running_var)
+    @staticmethod
+    def _fold(weight, bias, running_mean, running_var):
+        scale = weight.float() * (running_var.float() + 1e-5).rsqrt()
+        shift = bias.float() - running_mean.float() * scale
+        return torch.stack([scale, shift]).contiguous()
 
-        def make():
-            scale = self.weight.float() * (self.running_var.float() + 1e-5).rsqrt()
-            shift = self.bias.float() - self.running_mean.float() * scale
-            return torch.stack([scale, shift]).contiguous()
-        ss = E.derived(bufs, "fbn", make)
+    def folded(self):
+        ss = E.derived((self.weight, self.bias, self.running_mean, self.running_var), "fbn", FrozenBatchNorm2d._fold)
         return ss[0], ss[1]
 
 

@@ -8,8 +8,9 @@ kept as PARAMETER HOLDERS so state_dict keys match (`self_attn.in_proj_weight`, 
 their forward is never called — all math runs through layoutdetr_b200.functional.
 
 Token layout here is batch-major `[B*L, d_model]` (row = b*L + l) instead of the reference's
-`[L, B, d_model]`; results are layout-independent.  Dropout (p=0.1 in the reference) is not applied:
-deterministic eval semantics.
+`[L, B, d_model]`; results are layout-independent.  Dropout (p = 0.1: attention probabilities inside
+nn.MultiheadAttention, dropout1/2/3 on the sub-layer outputs, `dropout` after the FFN's ReLU; reference
+training/detr_transformer.py:185-194,210-214,270-285) is live in `.train()` mode, drawn in-kernel (layoutdetr_b200.rng).
 """
 import copy
 
@@ -18,6 +19,7 @@ import torch.nn as nn
 
 from .. import functional as Fn
 from .. import kernels as K
+from .. import rng as RNG
 
 LN_EPS = 1e-5
 
@@ -33,31 +35,43 @@ def _key_mask(mask):
     return mask.to(torch.uint8).contiguous()
 
 
-def self_attention_block(mha, norm, x, B, L, pos, key_mask):
-    """LN(x + out_proj(MHA(q = k = x + pos, v = x)))."""
+def layer_dropout_p(layer):
+    """Sub-layer dropout probability of a (this file's or torch's) transformer layer holder, 0 in eval mode."""
+    p = getattr(layer, "dropout_p", None)
+    if p is None:
+        d = getattr(layer, "dropout1", None)            # torch nn.TransformerEncoderLayer keeps nn.Dropout modules
+        p = d.p if isinstance(d, nn.Dropout) else 0.1
+    return RNG.p_of(layer.training, p)
+
+
+def self_attention_block(mha, norm, x, B, L, pos, key_mask, p_drop=0.0):
+    """LN(x + dropout(out_proj(MHA(q = k = x + pos, v = x)))); MHA drops attention probabilities with its own p."""
     E_ = mha.embed_dim
     H = mha.num_heads
     d = E_ // H
+    p_attn = RNG.p_of(mha.training, mha.dropout)
     if pos is not None:
         xp = Fn.add_bcast(x, pos)
         qk = Fn.linear(xp, mha.in_proj_weight, mha.in_proj_bias, rows=(0, 2 * E_))
         v = Fn.linear(x, mha.in_proj_weight, mha.in_proj_bias, rows=(2 * E_, 3 * E_))
-        ctx = Fn.attention(qk, qk, v, 0, E_, 0, B, H, L, L, d, key_mask=key_mask, mask_inf=True)
+        ctx = Fn.attention(qk, qk, v, 0, E_, 0, B, H, L, L, d, key_mask=key_mask, mask_inf=True, dropout_p=p_attn)
     else:
         qkv = Fn.linear(x, mha.in_proj_weight, mha.in_proj_bias)
-        ctx = Fn.attention(qkv, qkv, qkv, 0, E_, 2 * E_, B, H, L, L, d, key_mask=key_mask, mask_inf=True)
-    return Fn.linear_ln(ctx, x, mha.out_proj.weight, mha.out_proj.bias, norm.weight, norm.bias, LN_EPS)
+        ctx = Fn.attention(qkv, qkv, qkv, 0, E_, 2 * E_, B, H, L, L, d, key_mask=key_mask, mask_inf=True, dropout_p=p_attn)
+    return Fn.linear_ln(ctx, x, mha.out_proj.weight, mha.out_proj.bias, norm.weight, norm.bias, LN_EPS, dropout_p=p_drop)
 
 
-def ffn_block(layer, norm, x):
+def ffn_block(layer, norm, x, p_drop=0.0):
     h = Fn.linear(x, layer.linear1.weight, layer.linear1.bias, act=K.ACT_RELU)
-    return Fn.linear_ln(h, x, layer.linear2.weight, layer.linear2.bias, norm.weight, norm.bias, LN_EPS)
+    h = Fn.dropout(h, p_drop)
+    return Fn.linear_ln(h, x, layer.linear2.weight, layer.linear2.bias, norm.weight, norm.bias, LN_EPS, dropout_p=p_drop)
 
 
 def encoder_layer_forward(layer, x, B, L, pos, key_mask):
     """Works for both this file's TransformerEncoderLayer and torch's nn.TransformerEncoderLayer holders."""
-    x = self_attention_block(layer.self_attn, layer.norm1, x, B, L, pos, key_mask)
-    return ffn_block(layer, layer.norm2, x)
+    p = layer_dropout_p(layer)
+    x = self_attention_block(layer.self_attn, layer.norm1, x, B, L, pos, key_mask, p)
+    return ffn_block(layer, layer.norm2, x, p)
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -69,6 +83,7 @@ class TransformerEncoderLayer(nn.Module):
         self.linear2 = nn.Linear(dim_feedforward, d_model)
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
 
 
 class TransformerDecoderLayer(nn.Module):
@@ -82,10 +97,12 @@ class TransformerDecoderLayer(nn.Module):
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
         self.norm3 = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
 
     def forward(self, tgt, memory, memory_pos, B, L, S, tgt_key_mask):
         """tgt [B*L, d], memory [B*S, d], memory_pos = memory + pos [B*S, d] (all bf16)."""
-        tgt = self_attention_block(self.self_attn, self.norm1, tgt, B, L, None, tgt_key_mask)
+        p = layer_dropout_p(self)
+        tgt = self_attention_block(self.self_attn, self.norm1, tgt, B, L, None, tgt_key_mask, p)
         mha = self.multihead_attn
         E_ = mha.embed_dim
         H = mha.num_heads
@@ -93,9 +110,9 @@ class TransformerDecoderLayer(nn.Module):
         q = Fn.linear(tgt, mha.in_proj_weight, mha.in_proj_bias, rows=(0, E_))
         k = Fn.linear(memory_pos, mha.in_proj_weight, mha.in_proj_bias, rows=(E_, 2 * E_))
         v = Fn.linear(memory, mha.in_proj_weight, mha.in_proj_bias, rows=(2 * E_, 3 * E_))
-        ctx = Fn.attention(q, k, v, 0, 0, 0, B, H, L, S, d, key_mask=None, mask_inf=True)
-        tgt = Fn.linear_ln(ctx, tgt, mha.out_proj.weight, mha.out_proj.bias, self.norm2.weight, self.norm2.bias, LN_EPS)
-        return ffn_block(self, self.norm3, tgt)
+        ctx = Fn.attention(q, k, v, 0, 0, 0, B, H, L, S, d, key_mask=None, mask_inf=True, dropout_p=RNG.p_of(mha.training, mha.dropout))
+        tgt = Fn.linear_ln(ctx, tgt, mha.out_proj.weight, mha.out_proj.bias, self.norm2.weight, self.norm2.bias, LN_EPS, dropout_p=p)
+        return ffn_block(self, self.norm3, tgt, p)
 
 
 class TransformerEncoder(nn.Module):

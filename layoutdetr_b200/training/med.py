@@ -6,8 +6,10 @@ training/med.py:361).  Module / parameter names reproduce the reference state_di
 (`embeddings.word_embeddings.weight`, `encoder.layer.{i}.attention.self.query.weight`, ...,
 `cls.predictions.decoder.weight` tied to the word embeddings) so checkpoints load by name.
 
-Dropout (hidden 0.1 / attention 0.1 in configs/med_config.json) is not applied: the kernels
-implement the deterministic (eval / p=0) semantics the parity contract is stated in.
+Dropout (hidden 0.1 / attention-probability 0.1, configs/med_config.json:5,7; reference training/med.py:96,213,240,318)
+is live whenever the module is in `.train()` mode — as in the reference's training loop, also inside the frozen text
+encoder (training/training_loop.py:133-134) — and is drawn in-kernel from the Philox stream of layoutdetr_b200.rng.
+`.eval()` (G_ema, metrics, parity tests) gives the deterministic path.
 """
 import json
 import math
@@ -18,6 +20,7 @@ import torch.nn as nn
 
 from .. import functional as Fn
 from .. import kernels as K
+from .. import rng as RNG
 
 
 class BertConfig:
@@ -59,11 +62,13 @@ class BertEmbeddings(nn.Module):
         self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
         self.eps = config.layer_norm_eps
         self.pad_token_id = config.pad_token_id
+        self.hidden_dropout_prob = config.hidden_dropout_prob
 
     def forward(self, input_ids):
         B, T = input_ids.shape
-        return Fn.EmbedLNFn.apply(input_ids.contiguous(), self.word_embeddings.weight, self.position_embeddings.weight,
-                                  self.LayerNorm.weight, self.LayerNorm.bias, T, self.eps, self.pad_token_id)
+        y = Fn.EmbedLNFn.apply(input_ids.contiguous(), self.word_embeddings.weight, self.position_embeddings.weight,
+                               self.LayerNorm.weight, self.LayerNorm.bias, T, self.eps, self.pad_token_id)
+        return Fn.dropout(y, RNG.p_of(self.training, getattr(self, "hidden_dropout_prob", 0.1)))     # training/med.py:96
 
 
 class BertSelfAttention(nn.Module):
@@ -114,19 +119,23 @@ class BertLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
         self.eps = config.layer_norm_eps
+        self.hidden_dropout_prob = config.hidden_dropout_prob
+        self.attention_probs_dropout_prob = config.attention_probs_dropout_prob
 
     def forward(self, x, B, T, key_mask, causal):
         """x: bf16 [B*T, hidden].  Post-norm BERT layer (reference training/med.py:336-386)."""
         sa = self.attention.self
         H, d = sa.num_attention_heads, sa.attention_head_size
+        p_h = RNG.p_of(self.training, getattr(self, "hidden_dropout_prob", 0.1))                     # :240, :318
+        p_a = RNG.p_of(self.training, getattr(self, "attention_probs_dropout_prob", 0.1))            # :213
         qkv = Fn.fused_linear(x, (sa.query, sa.key, sa.value))
         ctx = Fn.attention(qkv, qkv, qkv, 0, H * d, 2 * H * d, B, H, T, T, d, 1.0 / math.sqrt(d),
-                           key_mask=key_mask, mask_inf=False, causal=causal)
+                           key_mask=key_mask, mask_inf=False, causal=causal, dropout_p=p_a)
         so = self.attention.output
-        h = Fn.linear_ln(ctx, x, so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias, self.eps)
+        h = Fn.linear_ln(ctx, x, so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias, self.eps, dropout_p=p_h)
         inter = Fn.linear(h, self.intermediate.dense.weight, self.intermediate.dense.bias, act=K.ACT_GELU)
         o = self.output
-        return Fn.linear_ln(inter, h, o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias, self.eps)
+        return Fn.linear_ln(inter, h, o.dense.weight, o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias, self.eps, dropout_p=p_h)
 
 
 class BertEncoder(nn.Module):

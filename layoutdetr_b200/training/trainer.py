@@ -7,6 +7,8 @@ Differences from the reference are mechanical, not numerical:
   * the EMA skips parameters that cannot change (the frozen text encoder) — lerp(p, p, beta) == p;
   * Greg / Dreg are no-ops at the reference defaults (pl_weight = r1_gamma = 0: zero_grad + an optimizer step
     over parameters without gradients), so they launch nothing;
+  * dropout (G / D in `.train()` as in training_loop.py:133-134) is drawn in-kernel from a device-resident Philox state that is
+    advanced once per iteration inside the captured graph (rng.py); modules in `.eval()` give the deterministic iteration;
   * independent parts of the iteration run on parallel CUDA streams (lanes.py): the frozen text-encoder calls, the
     branches of a forward pass that do not feed each other, and the real-sample discriminator pass (which does not
     depend on G) next to Gmain.  Same kernels, same operands; `LD_LANES=0` gives the single-stream schedule.
@@ -16,6 +18,7 @@ import copy
 import torch
 
 from .. import engine as E
+from .. import rng as RNG
 from ..flat import FlatParams
 from ..lanes import LANES
 from . import networks_detr as nd
@@ -101,6 +104,8 @@ class Trainer:
         """Start of an iteration: per-iteration caches, and with lanes on: refresh everything derived from the weights on
         this stream, issue the five text-encoder calls on the T lane and the real-sample discriminator pass on the R lane."""
         nd.new_iteration()
+        if self.G.training or self.D.training:
+            RNG.advance(self.device)         # fresh dropout masks every iteration, also under CUDA-graph replay (sites are baked in)
         self._iter_open = True
         self._real_issued = False
         self._real_lane = self._text_lane = None

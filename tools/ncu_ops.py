@@ -47,8 +47,23 @@ p = torch.randn(n, device=dev); gr = torch.randn(n, device=dev); m = torch.zeros
 p16 = torch.empty(n, dtype=torch.bfloat16, device=dev)
 
 
+# LM text-decoder attention backward (128 sequences, causal): fused ld_attention_bwd
+Bd = 128
+qkv_d = torch.randn((Bd * T, 3 * H * d), device=dev).to(torch.bfloat16)
+kmd = torch.zeros((Bd, T), dtype=torch.uint8, device=dev); kmd[:, 40:] = 1
+lse_d = torch.empty((Bd * H, T), dtype=torch.float32, device=dev)
+O_d = K.attention_fwd(qkv_d, 0, qkv_d, H * d, qkv_d, 2 * H * d, Bd, H, T, T, d, d ** -0.5, key_mask=kmd, causal=True, lse_out=lse_d)
+dO_d = torch.randn_like(O_d)
+dq_d = torch.empty_like(qkv_d)
+Pd_d = torch.empty((Bd * H, T, T), dtype=torch.bfloat16, device=dev)
+dS_d = torch.empty_like(Pd_d)
+
 OPS = [
     ("attention_bert", lambda: K.attention_fwd(qkv, 0, qkv, H * d, qkv, 2 * H * d, B, H, T, T, d, d ** -0.5, key_mask=km)),
+    ("attention_bert_dropout", lambda: K.attention_fwd(qkv, 0, qkv, H * d, qkv, 2 * H * d, B, H, T, T, d, d ** -0.5, key_mask=km,
+                                                       dropout_p=0.1, rng_site=7)),
+    ("attention_bert_bwd", lambda: K.attention_bwd(qkv_d, 0, qkv_d, H * d, qkv_d, 2 * H * d, O_d, dO_d, lse_d, dq_d, Pd_d, dS_d, Bd, H, T, T,
+                                                   d, d ** -0.5, key_mask=kmd, causal=True)),
     ("attention_detr_cross", lambda: K.attention_fwd(q2, 0, kv2, 0, kv2, 256, 16, 8, 10, 64, 32, 32 ** -0.5)),
     ("layernorm_res", lambda: K.layernorm_fwd(x_ln, g, b, 1e-12, residual=res)),
     ("bias_act", lambda: ba.bias_act(img, bias, act="lrelu")),
