@@ -22,7 +22,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("LAYOUTDETR_SYNTHETIC_TOKENIZER", "1")
+os.environ.setdefault("LAYOUTDETR_SYNTHETIC_TOKENIZER", "1")       # no vocabulary / checkpoint files on the GPU box:
+os.environ.setdefault("LAYOUTDETR_SYNTHETIC_WEIGHTS", "1")         # synthetic data AND synthetic weights, said so in "data"
 
 GFLOP_PER_SAMPLE = 3186.3          # dense fwd+bwd FLOPs of one training iteration, per sample
 METRIC = "layout samples/sec @ bs16 256^2 8-query (full G+D training iteration)"

@@ -232,11 +232,11 @@ int ld_ema_flat(float* p_ema, const float* p, void* p_ema_bf16, int64_t n, float
  * :213) and nn.MultiheadAttention as called by training/detr_transformer.py:208,273,277.  q / k / v: bf16 row-major [B*L, ld]
  * buffers, head h in columns h*d .. h*d+d of the given base; o: bf16 [B*Lq, ldo].  key_mask [B, Lk] (1 = masked) adds -10000
  * (mask_inf = 0) or -inf.  For the backward pass: lse_out (optional) fp32 [B*H, Lq] = log2-domain log-sum-exp of the scaled +
- * masked scores (max2 + log2(sum 2^(s2 - max2)), s2 = s * log2 e), consumed by ld_attention_bwd; p_out (optional, legacy) bf16
- * [B*H, Lq, ldp] normalised probabilities.  dropout_p > 0: probabilities are dropped with the Philox mask of
- * (rng_state = device {seed_lo, seed_hi, step, 0}, rng_site), element (b, h, row, col) -> group ((b*H+h)*Lq+row)*32 + col/8. */
+ * masked scores (max2 + log2(sum 2^(s2 - max2)), s2 = s * log2 e), consumed by ld_attention_bwd.  dropout_p > 0: probabilities
+ * are dropped with the Philox mask of (rng_state = device {seed_lo, seed_hi, step, 0}, rng_site), element (b, h, row, col) ->
+ * group ((b*H+h)*Lq+row)*32 + col/8. */
 int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                     void* o, int64_t ldo, void* p_out, int64_t ldp, float* lse_out,
+                     void* o, int64_t ldo, float* lse_out,
                      int B, int H, int Lq, int Lk, int d, float scale, const uint8_t* key_mask, int mask_inf, int causal,
                      float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
 /* Fused attention backward, the adjoint of ld_attention_fwd (same shape limits, same mask / dropout arguments): recomputes the

@@ -213,16 +213,15 @@ def _rng_ptr(dropout_p, device):
 
 
 def attention_fwd(q_t, q_off, k_t, k_off, v_t, v_off, B, H, Lq, Lk, d, scale, key_mask=None, mask_inf=False, causal=False,
-                  P_out=None, lse_out=None, dropout_p=0.0, rng_site=0):
+                  lse_out=None, dropout_p=0.0, rng_site=0):
     """Fused attention forward. q_t/k_t/v_t: bf16 [B*L, ld] buffers (may alias), head h of q at columns q_off + h*d.
-    Returns O bf16 [B*Lq, H*d]; fills lse_out [B*H, Lq] (log2-domain log-sum-exp, for attention_bwd) and / or the legacy
-    P_out [B*H, Lq, pad8(Lk)] with the probabilities if given."""
+    Returns O bf16 [B*Lq, H*d]; fills lse_out [B*H, Lq] (log2-domain log-sum-exp, for attention_bwd) if given."""
     _cuda(q_t, k_t, v_t)
     O = torch.empty((B * Lq, H * d), dtype=torch.bfloat16, device=q_t.device)
     check(lib().ld_attention_fwd(c_void_p(q_t.data_ptr() + 2 * q_off), c_int64(q_t.stride(0)),
                                  c_void_p(k_t.data_ptr() + 2 * k_off), c_int64(k_t.stride(0)),
                                  c_void_p(v_t.data_ptr() + 2 * v_off), c_int64(v_t.stride(0)),
-                                 _p(O), c_int64(H * d), _p(P_out), c_int64(P_out.stride(1) if P_out is not None else 0), _p(lse_out),
+                                 _p(O), c_int64(H * d), _p(lse_out),
                                  c_int(B), c_int(H), c_int(Lq), c_int(Lk), c_int(d), c_float(scale), _p(key_mask),
                                  c_int(1 if mask_inf else 0), c_int(1 if causal else 0), c_float(dropout_p),
                                  _rng_ptr(dropout_p, q_t.device), ctypes.c_uint32(rng_site), _stream()), "ld_attention_fwd")

@@ -1,45 +1,47 @@
-"""Drop-in for the reference's torch_utils/ops/fma.py: fma(a, b, c) = a * b + c as one kernel with
-broadcasting, with the reference's gradient rules (:27-60)."""
+"""Drop-in for the reference's torch_utils/ops/fma.py (`fma(a, b, c) = a * b + c`, reference :16-60): one broadcasting kernel
+(ld_fma_f32) forward; the gradients are products reduced back to each operand's shape."""
 import torch
 
 from ... import kernels as K
 
 
-def fma(a, b, c):
-    return _FusedMultiplyAdd.apply(a, b, c)
+def _sum_to_shape(t, shape):
+    """Reduce a broadcast result back to the operand shape `shape`: sum over the leading axes the operand does not have and
+    over every axis where it has extent 1."""
+    shape = tuple(shape)
+    lead = t.ndim - len(shape)
+    if lead < 0:
+        raise ValueError("cannot reduce %s to %s" % (tuple(t.shape), shape))
+    if lead:
+        t = t.sum(dim=tuple(range(lead)))
+    ones = tuple(i for i, (have, want) in enumerate(zip(t.shape, shape)) if want == 1 and have != 1)
+    if ones:
+        t = t.sum(dim=ones, keepdim=True)
+    if tuple(t.shape) != shape:
+        raise ValueError("gradient of shape %s does not reduce to %s" % (tuple(t.shape), shape))
+    return t
 
 
-class _FusedMultiplyAdd(torch.autograd.Function):
+class _Fma(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, c):
         if not a.is_cuda:
             raise RuntimeError("layoutdetr_b200 fma: CUDA tensors only (no CPU fallback)")
-        shape = torch.broadcast_shapes(a.shape, b.shape, c.shape)
-        out = K.fma_f32(a.float().broadcast_to(shape).contiguous(), b.float(), c.float()).to(a.dtype)
+        full = torch.broadcast_shapes(a.shape, b.shape, c.shape)
+        y = K.fma_f32(a.float().broadcast_to(full).contiguous(), b.float(), c.float()).to(a.dtype)
         ctx.save_for_backward(a, b)
-        ctx.c_shape = c.shape
-        return out
+        ctx.shapes = (a.shape, b.shape, c.shape)
+        return y
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dy):
         a, b = ctx.saved_tensors
-        da = db = dc = None
-        if ctx.needs_input_grad[0]:
-            da = _unbroadcast(dout * b, a.shape)
-        if ctx.needs_input_grad[1]:
-            db = _unbroadcast(dout * a, b.shape)
-        if ctx.needs_input_grad[2]:
-            dc = _unbroadcast(dout, ctx.c_shape)
-        return da, db, dc
+        sa, sb, sc = ctx.shapes
+        need_a, need_b, need_c = ctx.needs_input_grad
+        return (_sum_to_shape(dy * b, sa) if need_a else None,
+                _sum_to_shape(dy * a, sb) if need_b else None,
+                _sum_to_shape(dy, sc) if need_c else None)
 
 
-def _unbroadcast(x, shape):
-    extra_dims = x.ndim - len(shape)
-    assert extra_dims >= 0
-    dim = [i for i in range(x.ndim) if x.shape[i] > 1 and (i < extra_dims or shape[i - extra_dims] == 1)]
-    if len(dim):
-        x = x.sum(dim=dim, keepdim=True)
-    if extra_dims:
-        x = x.reshape(-1, *x.shape[extra_dims + 1:])
-    assert x.shape == shape
-    return x
+def fma(a, b, c):
+    return _Fma.apply(a, b, c)

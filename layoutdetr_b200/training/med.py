@@ -13,7 +13,9 @@ encoder (training/training_loop.py:133-134) — and is drawn in-kernel from the 
 """
 import json
 import math
+import os
 import types
+import warnings
 
 import torch
 import torch.nn as nn
@@ -51,6 +53,80 @@ class BertConfig:
     @classmethod
     def default(cls):
         return cls()
+
+
+# ------------------------------------------------------------------------------------------------
+# Pretrained weights.  The reference builds both BERT stacks with `from_pretrained('bert-base-uncased', config=...)`
+# (training/networks_detr.py:92,124; training/med.py via transformers.PreTrainedModel) and then freezes the text encoder
+# (training/training_loop.py:283): without the checkpoint G and D would train against a frozen RANDOM encoder.  So:
+# a local Hugging Face checkpoint (a directory, or the hub cache, never the network) is loaded by parameter name — the
+# module tree mirrors the reference's — and its absence is an error unless synthetic weights were asked for explicitly
+# (LAYOUTDETR_SYNTHETIC_WEIGHTS=1; LAYOUTDETR_SYNTHETIC_TOKENIZER=1 implies it: tests, bench.py, smoke()).
+def synthetic_weights_allowed():
+    return os.environ.get("LAYOUTDETR_SYNTHETIC_WEIGHTS", "0") == "1" or os.environ.get("LAYOUTDETR_SYNTHETIC_TOKENIZER", "0") == "1"
+
+
+def _find_checkpoint_file(name):
+    names = ("model.safetensors", "pytorch_model.bin")
+    if os.path.isdir(name):
+        for fn in names:
+            if os.path.exists(os.path.join(name, fn)):
+                return os.path.join(name, fn)
+        return None
+    try:
+        from transformers.utils import cached_file
+    except Exception:
+        return None
+    for fn in names:
+        try:
+            path = cached_file(name, fn, local_files_only=True, _raise_exceptions_for_missing_entries=False,
+                               _raise_exceptions_for_connection_errors=False)
+        except Exception:
+            path = None
+        if path and os.path.exists(path):
+            return path
+    return None
+
+
+def _read_checkpoint(path):
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=True)
+
+
+def load_pretrained_bert(model, name, strip_prefix):
+    """Copy every tensor of the local checkpoint `name` whose (normalised) key and shape match a parameter / buffer of
+    `model`; -> number of tensors loaded.  `strip_prefix`: 'bert.' for the bare encoder (BertModel), '' for the LM-head model."""
+    path = _find_checkpoint_file(name)
+    if path is None:
+        if synthetic_weights_allowed():
+            return 0
+        raise FileNotFoundError(
+            "pretrained checkpoint %r not found locally (a directory with model.safetensors / pytorch_model.bin, or the Hugging Face "
+            "cache). The reference initialises the BERT text encoder / decoder from it and freezes the encoder; refusing to fall "
+            "back to random weights silently. Provide the checkpoint, pass --resume with a trained pickle after constructing with "
+            "LAYOUTDETR_SYNTHETIC_WEIGHTS=1, or set LAYOUTDETR_SYNTHETIC_WEIGHTS=1 for synthetic-weight runs." % (name,))
+    src = _read_checkpoint(path)
+    own = dict(model.state_dict())
+    loaded = 0
+    with torch.no_grad():
+        for k, v in src.items():
+            k = k.replace(".gamma", ".weight").replace(".beta", ".bias")             # TF-converted BERT checkpoints
+            if strip_prefix and k.startswith(strip_prefix):
+                k = k[len(strip_prefix):]
+            elif strip_prefix == "" and not (k.startswith("bert.") or k.startswith("cls.")):
+                k = "bert." + k                                                          # bare-encoder checkpoint into the LM model
+            t = own.get(k)
+            if t is not None and tuple(t.shape) == tuple(v.shape):
+                t.copy_(v.to(t.dtype))
+                loaded += 1
+    if loaded == 0:
+        raise RuntimeError("checkpoint %s has no tensor matching %s" % (path, type(model).__name__))
+    missing = [k for k in own if "crossattention" not in k and "position_ids" not in k]
+    if loaded < len(missing) // 2:
+        warnings.warn("only %d of %d tensors of %s were found in %s" % (loaded, len(missing), type(model).__name__, path))
+    return loaded
 
 
 class BertEmbeddings(nn.Module):
@@ -168,8 +244,10 @@ class BertModel(nn.Module):
 
     @classmethod
     def from_pretrained(cls, name, config=None, **kw):
-        # no network / no checkpoint files on the build and GPU boxes: random init, weights arrive by state_dict
-        return cls(config, **kw)
+        """Local checkpoint by parameter name (see load_pretrained_bert); random init only under LAYOUTDETR_SYNTHETIC_WEIGHTS=1."""
+        model = cls(config, **kw)
+        load_pretrained_bert(model, name, "bert.")
+        return model
 
     def resize_token_embeddings(self, n):
         old = self.embeddings.word_embeddings
@@ -247,7 +325,10 @@ class BertLMHeadModel(nn.Module):
 
     @classmethod
     def from_pretrained(cls, name, config=None, **kw):
-        return cls(config, **kw)
+        model = cls(config, **kw)
+        load_pretrained_bert(model, name, "")
+        model._tie()
+        return model
 
     def resize_token_embeddings(self, n):
         old_n = self.bert.embeddings.word_embeddings.num_embeddings

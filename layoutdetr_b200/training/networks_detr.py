@@ -45,20 +45,25 @@ def build_backbone():
 
 
 def init_tokenizer():
-    """BertTokenizer('bert-base-uncased') + [DEC]/[ENC] when a local vocab exists (reference training/blip.py:190),
-    otherwise the deterministic synthetic tokenizer with the same special-token layout."""
+    """BertTokenizer('bert-base-uncased') + [DEC] / [ENC] from a LOCAL vocabulary (reference training/blip.py:190-195).
+    LAYOUTDETR_SYNTHETIC_TOKENIZER=1 selects the deterministic synthetic tokenizer (same special-token layout, ids unrelated
+    to any real checkpoint) — an explicit opt-in: a missing vocabulary is an error, never a silent change of token ids."""
+    if os.environ.get("LAYOUTDETR_SYNTHETIC_TOKENIZER", "0") == "1":
+        from ..synthetic import SyntheticTokenizer
+        return SyntheticTokenizer()
     try:
-        if os.environ.get("LAYOUTDETR_SYNTHETIC_TOKENIZER", "0") != "1":
-            from transformers import BertTokenizer
-            tok = BertTokenizer.from_pretrained("bert-base-uncased", local_files_only=True)
-            tok.add_special_tokens({"bos_token": "[DEC]"})
-            tok.add_special_tokens({"additional_special_tokens": ["[ENC]"]})
-            tok.enc_token_id = tok.additional_special_tokens_ids[0]
-            return tok
-    except Exception:
-        pass
-    from ..synthetic import SyntheticTokenizer
-    return SyntheticTokenizer()
+        from transformers import BertTokenizer
+        tok = BertTokenizer.from_pretrained("bert-base-uncased", local_files_only=True)
+        if tok.vocab_size != 30522:          # transformers >= 5 hands back an EMPTY tokenizer when no vocabulary file is cached
+            raise FileNotFoundError("vocab.txt of bert-base-uncased not found (tokenizer has %d entries)" % tok.vocab_size)
+    except Exception as e:
+        raise RuntimeError("the bert-base-uncased vocabulary is not available locally (%s: %s). Token ids must match the checkpoint "
+                           "the text encoder was trained with; set LAYOUTDETR_SYNTHETIC_TOKENIZER=1 only for synthetic-weight runs "
+                           "(tests, bench.py)." % (type(e).__name__, e)) from e
+    tok.add_special_tokens({"bos_token": "[DEC]"})
+    tok.add_special_tokens({"additional_special_tokens": ["[ENC]"]})
+    tok.enc_token_id = tok.convert_tokens_to_ids("[ENC]")
+    return tok
 
 
 def _med_config(path):
@@ -178,6 +183,19 @@ def _encode_text_now(module, text):
         module._cls_cache = (key, feat)
         return feat
     return enc.cls_features(ids, mask).contiguous()
+
+
+def trimmed_widths(module, bbox_text, padding_mask_cpu, device):
+    """(encoder width, decoder width) `text_trim` would use for this batch — host-side, from the tokenizer's attention mask
+    (the front end's cached copy); the key of anything that bakes these widths in (trainer.GraphedStep)."""
+    if not module.text_trim:
+        return (module.max_text_length, module.max_text_length)
+    mask = module._front()(bbox_text, device)["mask_cpu"]
+    T = mask.shape[1]
+    t_enc = min(T, (int(mask.sum(1).max()) + 7) // 8 * 8)
+    valid = np.flatnonzero(~padding_mask_cpu.numpy().astype(bool).reshape(-1))
+    t_dec = min(T, (int(mask[valid].sum(1).max()) + 7) // 8 * 8) if len(valid) else T
+    return (t_enc, t_dec)
 
 
 def prefetch_text(modules, bbox_text, device):

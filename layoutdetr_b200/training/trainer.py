@@ -201,15 +201,29 @@ class GraphedStep:
     a graph, so graphs are keyed on them; everything data-dependent is read from static device buffers that `run` refreshes
     before each replay: images, boxes, classes, z, token ids / masks / lengths and the LM-loss normalisers."""
 
-    def __init__(self, trainer):
+    def __init__(self, trainer, max_graphs=None, capture_after=None):
+        import collections
+        import os
         self.tr = trainer
-        self.graphs = {}
+        self.graphs = collections.OrderedDict()    # key -> entry, least recently used first
         self.stream = LANES.main_stream()          # warm-up + capture stream = the main lane
+        # A graph bakes in which slots are valid (and, with text_trim, the token width).  Synthetic / bucketed data has a
+        # handful of such keys; real data can have one per batch, and a capture costs 2-3 warm-up iterations plus a private
+        # memory pool.  So: at most `max_graphs` graphs are kept (least recently used is dropped), and a key is only captured
+        # once it has been seen `capture_after` times — until then (and for one-off keys) the iteration runs eagerly.
+        self.max_graphs = int(os.environ.get("LD_MAX_GRAPHS", "8")) if max_graphs is None else max_graphs
+        self.capture_after = int(os.environ.get("LD_GRAPH_CAPTURE_AFTER", "1")) if capture_after is None else capture_after
+        self._seen = collections.Counter()
+        self.eager_steps = 0
 
     def _key(self, host_batch):
         pm = host_batch["padding_mask"]
         G = self.tr.G
-        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup),
+        widths = ()
+        if G.text_trim or self.tr.D.text_trim:     # the trimmed token widths are baked into the captured GEMM shapes
+            widths = tuple(nd.trimmed_widths(m, host_batch["bbox_text"], pm, self.tr.device) for m in (G, self.tr.D))
+        return (tuple(host_batch["background"].shape), pm.numpy().tobytes(), bool(G.text_trim), bool(G.text_dedup), widths,
+                bool(G.training), bool(self.tr.D.training),
                 LANES.level, LANES.text_ctas, LANES.lm_ctas, LANES.high_priority, LANES.dry, LANES.real_first)
 
     def _refresh_host_derived(self, st, host_mask):
@@ -276,7 +290,7 @@ class GraphedStep:
 
     def run_static(self):
         """Replay the captured iteration on whatever the static input buffers currently hold (inputs resident in HBM)."""
-        ent = next(iter(self.graphs.values()))
+        ent = next(reversed(self.graphs.values()))               # most recently used graph
         self._replay(ent)
         return ent["out"]
 
@@ -286,6 +300,17 @@ class GraphedStep:
         tr = self.tr
         key = self._key(host_batch)
         ent = self.graphs.get(key)
+        if ent is not None:
+            self.graphs.move_to_end(key)
+        else:
+            self._seen[key] += 1
+            if self._seen[key] < self.capture_after:             # not worth a capture yet: plain eager iteration
+                self.eager_steps += 1
+                batch = {k: (v.to(tr.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
+                return tr.iteration(batch, z_g, z_d)
+            while len(self.graphs) >= max(1, self.max_graphs):   # drop the least recently used graph (and its memory pool)
+                _, old = self.graphs.popitem(last=False)
+                old.clear()
         if ent is None:
             st = {k: (v.to(tr.device) if torch.is_tensor(v) else v) for k, v in host_batch.items()}
             st["z_g"], st["z_d"] = z_g.clone(), z_d.clone()
@@ -322,7 +347,10 @@ class GraphedStep:
                     torch.cuda.synchronize()
             out = {ph: {k: v for k, v in terms.items()} for ph, terms in tr.loss.last.items()}
             tr.segmented = False
-            ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0)
+            # host-derived device tensors the captured kernels read (valid-slot indices): owned by the entry, so the module-level
+            # caches in networks_detr may be recycled without pulling memory from under a graph
+            keep = [nd.valid_index(st["padding_mask"])]
+            ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0, keep=keep)
             self.graphs[key] = ent
             self._restore(snap, st)
             self._replay(ent)                                    # the first real step on this batch

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# no vocabulary / checkpoint files travel with the repo: every test runs on the synthetic tokenizer and synthetic weights
+os.environ.setdefault("LAYOUTDETR_SYNTHETIC_TOKENIZER", "1")
+os.environ.setdefault("LAYOUTDETR_SYNTHETIC_WEIGHTS", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -37,11 +37,17 @@ def test_fused_attention_forward(Lq, Lk, d, H, mask_inf, causal, use_mask):
         km[2, -1] = 1
     scale = 1.0 / d ** 0.5
     Lkp = (Lk + 7) // 8 * 8
-    P = torch.zeros((B * H, Lq, Lkp), dtype=torch.bfloat16, device="cuda")
     lse = torch.zeros((B * H, Lq), dtype=torch.float32, device="cuda")
-    O = k.attention_fwd(qkv_q, H * d, kv, 0, kv, H * d, B, H, Lq, Lk, d, scale, key_mask=km, mask_inf=mask_inf, causal=causal, P_out=P)
+    O = k.attention_fwd(qkv_q, H * d, kv, 0, kv, H * d, B, H, Lq, Lk, d, scale, key_mask=km, mask_inf=mask_inf, causal=causal)
     O2 = k.attention_fwd(qkv_q, H * d, kv, 0, kv, H * d, B, H, Lq, Lk, d, scale, key_mask=km, mask_inf=mask_inf, causal=causal, lse_out=lse)
+    # the probabilities themselves: the backward kernel recomputes them from lse (dropout off: Pd == P)
+    P = torch.zeros((B * H, Lq, Lkp), dtype=torch.bfloat16, device="cuda")
+    dS = torch.zeros_like(P)
+    dq = torch.zeros_like(qkv_q)
+    k.attention_bwd(qkv_q, H * d, kv, 0, kv, H * d, O2, torch.zeros_like(O2), lse, dq, P, dS, B, H, Lq, Lk, d, scale, key_mask=km,
+                    mask_inf=mask_inf, causal=causal)
     torch.cuda.synchronize()
+    assert float(dS.float().abs().max()) == 0.0 and float(dq.float().abs().max()) == 0.0       # zero upstream gradient
     q = qkv_q[:, H * d:2 * H * d]
     ref_o, ref_p = _ref(q, kv[:, :H * d], kv[:, H * d:], B, H, Lq, Lk, d, scale, km, mask_inf, causal)
     sc = float(ref_o.abs().max())
