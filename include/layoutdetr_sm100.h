@@ -239,6 +239,8 @@ int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      void* o, int64_t ldo, float* lse_out,
                      int B, int H, int Lq, int Lk, int d, float scale, const uint8_t* key_mask, int mask_inf, int causal,
                      float dropout_p, const uint32_t* rng_state, uint32_t rng_site, void* stream);
+/* Debug aid for ld_attention_fwd: per-tile event clocks of CTA 0 are written to dev_buf (int64 [64][16]); NULL switches it off. */
+int ld_debug_attention_trace(void* dev_buf);
 /* Fused attention backward, the adjoint of ld_attention_fwd (same shape limits, same mask / dropout arguments): recomputes the
  * probabilities from lse (the forward's lse_out), regenerates the dropout mask and produces
  *   dq      bf16 [B*Lq, lddq] at head h columns h*d..   dQ = dS K,  dS = P o (dropout'(dO V^T) - rowsum(dO o O)) * scale

@@ -23,6 +23,14 @@
 //                 through the free tail of X[c]), sweep 2 e = 2^(s - max) -> (dropout) -> bf16 into the swizzled P tile, fp32 row
 //                 sums (exchanged through the dead mask buffer); epilogue O * (1 / sum) -> bf16 -> swizzled X[c] -> TMA store
 //                 (row-per-thread 16-byte global stores were tried: 3072 half-used sectors per tile, 7.5 k cycles of LSU time).
+// Measured alternatives (B200, BERT launch, ncu; timelines from tools/attn_trace.py in profiles/r2_attn_timeline.txt):
+//   one thread per row, alternating MMA order, TMA store by a softmax thread      60.6 us
+//   two threads per row, direct 16-byte global stores of O                        64.2 us  (LSU-bound epilogue, 7.5 k cycles)
+//   + paired MMA order, O staged in X[c] and stored by the Q-producer thread      50.6 us  <- this file
+//   + both chains on the two q-tiles of one head sharing every K / V unit         67.6 us  (the chains run in lock step: the
+//       SIMT phase of both, 8 k cycles, is no longer hidden under the other chain's MMAs / loads)
+// What is left is the serial latency of a tile — O store 2-3 k cycles, Q load 3-4 k, QK^T 1.6 k + K-unit waits, softmax 4.6 k,
+// PV 1.6 k + V-unit waits — with only two tiles in flight; a third would need the P tile out of shared memory (TMEM-resident P).
 // Neither the fp32 scores nor the probabilities reach HBM; for the backward pass the kernel saves one float per row
 // (log2-domain log-sum-exp), from which ld_attention_bwd recomputes P.
 #include <cstdlib>
@@ -52,7 +60,15 @@ struct AfParams {
     __nv_bfloat16* O; long ldo;
     float* lse;                                // optional [B*H, Lq]: max2 + log2(sum) of the scaled + masked scores (log2 domain)
     const uint32_t* rng; uint32_t site, thresh16; float drop_scale;
+    long long* trace;                          // debug (ld_debug_attention_trace): per-tile event clocks of CTA 0, 16 slots per tile
 };
+
+// event slots of the trace: MMA thread 0..3, first softmax thread of the tile's chain 4..8, Q-producer thread 9..11
+enum { EV_QK_START = 0, EV_QK_ISSUED, EV_PV_START, EV_PV_ISSUED, EV_S_SEEN, EV_MAX_DONE, EV_P_DONE, EV_O_SEEN, EV_EPI_DONE,
+       EV_STAGED_SEEN, EV_STORE_READ, EV_Q_ISSUED };
+__device__ __forceinline__ void trace_ev(const AfParams& p, int tile, int ev) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tile < 64) p.trace[tile * 16 + ev] = clock64();
+}
 
 struct TileId { int b, h, m0; };
 __device__ __forceinline__ TileId decode(const AfParams& p, int t) {
@@ -139,15 +155,18 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
                 if (i >= 2) {                                    // O of the chain's previous tile: smem -> HBM
                     const TileId od = decode(p, (int)blockIdx.x + (i - 2) * (int)gridDim.x);
                     mbar_wait(&o_staged[c], (uint32_t)((k - 1) & 1));
+                    trace_ev(p, i - 2, EV_STAGED_SEEN);
                     for (int ch = 0; ch < p.dch; ++ch) tma_store_4d(&tmO, xa + ch * 16384, ch * 64, od.m0, od.h, od.b);
                     tma_store_commit();
                 }
                 if (i < n_local) {
                     const TileId id = decode(p, (int)blockIdx.x + i * (int)gridDim.x);
                     if (i >= 2) tma_store_wait_read();           // the store has read X[c]: it may take the next Q tile
+                    trace_ev(p, i, EV_STORE_READ);
                     mbar_arrive_expect_tx(&q_full[c], (uint32_t)p.dch * 16384u);
                     for (int ch = 0; ch < p.dch; ++ch)
                         tma_load_4d(x_s + c * AF_X_BYTES + ch * 16384, &tmQ, &q_full[c], ch * 64, id.m0, id.h, id.b);
+                    trace_ev(p, i, EV_Q_ISSUED);
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // stores complete before the CTA exits
@@ -162,6 +181,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
                 const int c = i & 1, k = i >> 1;
                 mbar_wait(&p_ready[c], (uint32_t)(k & 1));
                 tc_fence_after();
+                trace_ev(p, i, EV_PV_START);
                 const uint32_t pa = smem_u32(x_s + c * AF_X_BYTES);
                 const uint32_t tmem_o = tmem_base + (uint32_t)c * 256u;
                 for (int j = 0; j < p.nkb; ++j) {
@@ -178,12 +198,14 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
                     if (++stage == AF_RING) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&o_full[c]);
+                trace_ev(p, i, EV_PV_ISSUED);
             };
             auto qk = [&](int i) {                               // S = Q K^T of local tile i
                 const int c = i & 1, k = i >> 1;
                 if (k >= 1) { mbar_wait(&o_free[c], (uint32_t)((k - 1) & 1)); tc_fence_after(); }   // previous O of this chain drained
                 mbar_wait(&q_full[c], (uint32_t)(k & 1));
                 tc_fence_after();
+                trace_ev(p, i, EV_QK_START);
                 const uint32_t qa = smem_u32(x_s + c * AF_X_BYTES);
                 const uint32_t tmem_s = tmem_base + (uint32_t)c * 256u;
                 for (int ch = 0; ch < p.dch; ++ch) {             // S += Q[:, 64ch : 64ch+64] K[:, 64ch : 64ch+64]^T
@@ -200,6 +222,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
                     if (++stage == AF_RING) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&s_full[c]);
+                trace_ev(p, i, EV_QK_ISSUED);
             };
             for (int i = 0; i < n_local; i += 2) {
                 qk(i);
@@ -233,6 +256,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
             asm volatile("bar.sync %0, 256;" ::"r"(bar_all) : "memory");
             mbar_wait(&s_full[c], (uint32_t)(k & 1));
             tc_fence_after();
+            if (ct == 0) trace_ev(p, i, EV_S_SEEN);
             // ---- sweep 1: row max of s2 = acc * scale2 + mask2[col] (+ causal) over this thread's key blocks
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
             for (int j = jb; j < je; ++j) {
@@ -263,6 +287,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
             sts_f32(xmax_a + (half * 128 + r) * 4, mx);
             asm volatile("bar.sync %0, 256;" ::"r"(bar_all) : "memory");
             mx = fmaxf(lds_f32(xmax_a + r * 4), lds_f32(xmax_a + (128 + r) * 4));
+            if (ct == 0) trace_ev(p, i, EV_MAX_DONE);
             // the exchange words sit where sweep 2 of the upper half writes key block 3 of P: those writers wait (bar.sync) until
             // every thread of the chain has read its maxima (bar.arrive) — in practice never, block 3 is their last
             if (half == 0) asm volatile("bar.arrive %0, 256;" ::"r"(bar_xch) : "memory");
@@ -308,6 +333,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[c]);
+            if (ct == 0) trace_ev(p, i, EV_P_DONE);
             // ---- row sums of the two halves through the (now dead) mask buffer
             float sum = (sum0 + sum1) + (sum2 + sum3);
             asm volatile("bar.sync %0, 256;" ::"r"(bar_all) : "memory");         // every thread of the chain is done with the mask
@@ -320,6 +346,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
             //      This thread: every other 32-column block of its row.
             mbar_wait(&o_full[c], (uint32_t)(k & 1));
             tc_fence_after();
+            if (ct == 0) trace_ev(p, i, EV_O_SEEN);
             for (int c0 = 32 * half; c0 < p.dch * 64; c0 += 64) {
                 if (c0 >= p.d) break;                            // warp-uniform: zero-padded columns of head_dim < 64 (never stored)
                 uint32_t v[32];
@@ -343,6 +370,7 @@ attention_fwd_pipelined_kernel(const __grid_constant__ CUtensorMap tmQ, const __
                 mbar_arrive(&o_free[c]);                         // TMEM columns of this chain may take the next QK^T
                 mbar_arrive(&o_staged[c]);                       // O tile staged: the Q-producer thread stores it and reloads X[c]
             }
+            if (ct == 0) trace_ev(p, i, EV_EPI_DONE);
         }
     }
     tc_fence_before();
@@ -373,7 +401,12 @@ int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tm
     attention_fwd_pipelined_kernel<CAUSAL, DROPOUT><<<grid, AF_THREADS, AF_SMEM, stream>>>(tmQ, tmK, tmV, tmO, p);
     return 0;
 }
+long long* g_attention_trace = nullptr;
 }  // namespace
+
+// Debug aid: event clocks (clock64 of the SM running CTA 0) of the next ld_attention_fwd launches are written to `dev_buf`
+// ([64 tiles][16 events] int64, see the EV_* slots above; nullptr switches it off).  tools/attn_trace.py prints the timeline.
+extern "C" int ld_debug_attention_trace(void* dev_buf) { g_attention_trace = (long long*)dev_buf; return 0; }
 
 // q / k / v point at column 0 of head 0 inside row-major [B*L, ld] bf16 buffers (head h at columns h*d .. h*d+d).
 extern "C" int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
@@ -400,6 +433,7 @@ extern "C" int ld_attention_fwd(const void* q, int64_t ldq, const void* k, int64
     p.rng = rng_state; p.site = rng_site;
     p.thresh16 = dropout_p > 0.0f ? (uint32_t)(dropout_p * 65536.0f + 0.5f) : 0u;
     p.drop_scale = dropout_p > 0.0f ? 65536.0f / (65536.0f - (float)p.thresh16) : 1.0f;
+    p.trace = g_attention_trace;
     alignas(64) CUtensorMap tmQ, tmK, tmV, tmO;
     int e = make_map(&tmQ, q, ldq, d, Lq, H, B, 128); if (e) return e;
     e = make_map(&tmK, k, ldk, d, Lk, H, B, (uint32_t)p.ncols); if (e) return e;
