@@ -185,6 +185,29 @@ class Trainer:
             self.update_ema()
         return self.loss.last
 
+    def iteration_multi(self, batches, zs_g, zs_d, update_ema=True):
+        """One optimizer step per network over SEVERAL micro-batches (batch_gpu < batch_size // num_gpus: the gradient
+        accumulation of the reference loop, training_loop.py:286-301).  Eager and single-stream; the per-micro-batch text
+        front end makes a captured graph pointless here."""
+        if self.G.training or self.D.training:
+            RNG.advance(self.device)
+        with LANES.suspended():
+            for name, zs in (("G", zs_g), ("D", zs_d)):
+                mod = self.G if name == "G" else self.D
+                self.flat[name].zero_grad()
+                mod.requires_grad_(True)
+                mod.text_encoder.requires_grad_(False)
+                for batch, z in zip(batches, zs):
+                    nd.new_iteration()
+                    self._accumulate(name + "main", batch, z)
+                mod.requires_grad_(False)
+                self._phase_reduce(name)
+                self._phase_step(name)
+        self._warmed = True
+        if update_ema:
+            self.update_ema()
+        return self.loss.last
+
     def update_ema(self):
         ema_nimg = self.ema_kimg * 1000
         if self.ema_rampup is not None:

@@ -99,6 +99,31 @@ def gen_hungarian():
     print("hungarian goldens:", len(cases))
 
 
+def gen_maxiou():
+    """Reference `compute_maximum_iou` (metrics/metric_layoutnet.py:140-150, scipy + a multiprocessing pool) on two seeded sets of
+    layouts whose label multisets repeat, incl. groups of different sizes on the two sides (the reshape(N, M) quirk)."""
+    import numpy as np
+    import metrics.metric_layoutnet as mln          # the reference's (ref_shim.load() put the checkout first on sys.path)
+    rng = np.random.RandomState(5)
+    label_sets = [[0, 0, 1], [1, 2, 2, 2], [3], [0, 1, 2, 3, 4], [5, 5]]
+
+    def layouts(counts):
+        out = []
+        for ls, k in zip(label_sets, counts):
+            for _ in range(k):
+                n = len(ls)
+                b = np.stack([rng.uniform(0.2, 0.8, n), rng.uniform(0.2, 0.8, n), rng.uniform(0.1, 0.6, n), rng.uniform(0.05, 0.4, n)], 1)
+                perm = rng.permutation(n)
+                out.append((b[perm], np.array(ls)[perm]))
+        return out
+
+    l1, l2 = layouts([3, 2, 4, 1, 0]), layouts([2, 2, 4, 3, 2])
+    score = mln.compute_maximum_iou(l1, l2, n_jobs=1)
+    pack = lambda ls: [(torch.from_numpy(b.copy()), torch.from_numpy(l.copy())) for b, l in ls]
+    torch.save(dict(layouts_1=pack(l1), layouts_2=pack(l2), score=float(score)), os.path.join(GOLD, "maxiou_ref.pt"))
+    print("max-IoU golden:", score)
+
+
 def gen_eval():
     """Evaluation-sweep pieces of the reference: LayoutNet.extract_features (FID features, synthetic weights), per-layout
     IoU / DocSim, overlap / alignment, FeatureStats moments + the layout-FID formula."""
@@ -314,6 +339,7 @@ def main():
     ap.add_argument("--only-eval", action="store_true", help="regenerate tests/golden/eval_ref.pt only")
     ap.add_argument("--only-ragged", action="store_true", help="regenerate tests/golden/model_b3_ragged.pt only")
     ap.add_argument("--only-dataset", action="store_true", help="regenerate tests/golden/tiny_layout.zip + dataset_ref.pt only")
+    ap.add_argument("--only-maxiou", action="store_true", help="regenerate tests/golden/maxiou_ref.pt only")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     nd = ref_shim.load()
@@ -321,12 +347,16 @@ def main():
     if args.only_eval:
         gen_eval()
         return
+    if args.only_maxiou:
+        gen_maxiou()
+        return
     if args.only_dataset:
         gen_dataset()
         gen_sampler()
         return
     gen_ops()
     gen_hungarian()
+    gen_maxiou()
     gen_eval()
     gen_dataset()
     gen_sampler()

@@ -28,8 +28,19 @@ import metrics.metric_utils_layout as mul
 assert lfid.compute_layout_fid.__module__ == "layoutdetr_b200.metrics.sweep_entry" and mul.__file__.startswith(%r)
 assert oa.compute_overlap_alignment_laywise_IoU_layerwise_DocSim.__module__ == "layoutdetr_b200.metrics.sweep_entry"
 assert hasattr(cg, "no_weight_gradients") and misc.__file__.startswith(%r) and dnnlib.__file__.startswith(%r)
+import training.training_loop as tl, training.loss as tloss, metrics.metric_layoutnet as mln, inspect
+assert tl.training_loop.__module__ == "layoutdetr_b200.training.training_loop" and tloss.StyleGAN2Loss.__module__ == "layoutdetr_b200.training.loss"
+assert mln.generalized_iou_loss.__module__ == "layoutdetr_b200.metrics.metric_layoutnet" and hasattr(mln, "compute_iou_for_layout")
+import importlib.util
+spec = importlib.util.spec_from_file_location("_ref_tl", %r + "/training/training_loop.py")
+ref_src = open(spec.origin).read()
+import ast
+ref_fn = [n for n in ast.parse(ref_src).body if isinstance(n, ast.FunctionDef) and n.name == "training_loop"][0]
+ref_args = [a.arg for a in ref_fn.args.args]
+ours = list(inspect.signature(tl.training_loop).parameters)
+assert ours[:len(ref_args)] == ref_args, (ours, ref_args)          # same keyword arguments, same order (+ extensions at the end)
 print("OVERLAY_OK")
-''' % (REF, REF, REF)
+''' % (REF, REF, REF, REF)
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
         f.write(code)

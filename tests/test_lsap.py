@@ -46,3 +46,23 @@ def test_lsap_cuda_bit_exact():
         for i in range(0, 500, 7):
             r0, c0 = lsap.linear_sum_assignment(m[i], maximize=True)
             assert np.array_equal(r[i].cpu().numpy(), r0) and np.array_equal(col[i].cpu().numpy(), c0)
+
+
+def test_maximum_iou_oracle_matches_reference_golden():
+    """oracle restatement of compute_maximum_iou vs the value the reference's own function produced (gen_golden.py --only-maxiou)."""
+    from oracle import layoutdetr_oracle as O
+    g = golden("maxiou_ref.pt")
+    l1 = [(b.numpy(), l.numpy()) for b, l in g["layouts_1"]]
+    l2 = [(b.numpy(), l.numpy()) for b, l in g["layouts_2"]]
+    assert abs(O.compute_maximum_iou(l1, l2) - g["score"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_maximum_iou_cuda_matches_reference_golden():
+    """Product compute_maximum_iou (batched ld_lsap) vs the reference's value: assignments are bit-identical to scipy, the score
+    differs only by fp64 summation order."""
+    from layoutdetr_b200.metrics.metric_layoutnet import compute_maximum_iou
+    g = golden("maxiou_ref.pt")
+    l1 = [(b.numpy(), l.numpy()) for b, l in g["layouts_1"]]
+    l2 = [(b.numpy(), l.numpy()) for b, l in g["layouts_2"]]
+    assert abs(compute_maximum_iou(l1, l2) - g["score"]) < 1e-9
