@@ -28,12 +28,13 @@ def _fingerprint(G):
 
 
 def _cache_lookup(opts, key):
-    hit = (_cache["ref"] is not None and _cache["ref"]() is opts.G and _cache["key"] == key)
+    ref = _cache.get("ref")
+    hit = (ref is not None and ref() is opts.G and _cache.get("key") == key)
     if getattr(opts, "num_gpus", 1) > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
         flag = torch.tensor([1 if hit else 0], dtype=torch.int32, device=opts.device)
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)       # a hit only if EVERY rank hits
         hit = bool(int(flag.item()))
-    return _cache["res"] if hit else None
+    return _cache.get("res") if hit else None
 
 
 def rank_item_subset(num_items, num_gpus, rank):

@@ -44,7 +44,7 @@ def layer_dropout_p(layer):
     return RNG.p_of(layer.training, p)
 
 
-def self_attention_block(mha, norm, x, B, L, pos, key_mask, p_drop=0.0):
+def self_attention_block(mha, norm, x, B, L, pos, key_mask, p_drop=0.0, eps=LN_EPS):
     """LN(x + dropout(out_proj(MHA(q = k = x + pos, v = x)))); MHA drops attention probabilities with its own p."""
     E_ = mha.embed_dim
     H = mha.num_heads
@@ -58,20 +58,27 @@ def self_attention_block(mha, norm, x, B, L, pos, key_mask, p_drop=0.0):
     else:
         qkv = Fn.linear(x, mha.in_proj_weight, mha.in_proj_bias)
         ctx = Fn.attention(qkv, qkv, qkv, 0, E_, 2 * E_, B, H, L, L, d, key_mask=key_mask, mask_inf=True, dropout_p=p_attn)
-    return Fn.linear_ln(ctx, x, mha.out_proj.weight, mha.out_proj.bias, norm.weight, norm.bias, LN_EPS, dropout_p=p_drop)
+    return Fn.linear_ln(ctx, x, mha.out_proj.weight, mha.out_proj.bias, norm.weight, norm.bias, eps, dropout_p=p_drop)
 
 
-def ffn_block(layer, norm, x, p_drop=0.0):
-    h = Fn.linear(x, layer.linear1.weight, layer.linear1.bias, act=K.ACT_RELU)
+def layer_activation(layer):
+    """ReLU (DETR, the discriminator's torch stacks) or exact GELU (the ViT stack, networks_vit.py:178) of a layer holder."""
+    fn = getattr(layer, "activation", None)
+    name = getattr(fn, "__name__", str(fn)).lower()
+    return K.ACT_GELU if "gelu" in name else K.ACT_RELU
+
+
+def ffn_block(layer, norm, x, p_drop=0.0, act=K.ACT_RELU, eps=LN_EPS):
+    h = Fn.linear(x, layer.linear1.weight, layer.linear1.bias, act=act)
     h = Fn.dropout(h, p_drop)
-    return Fn.linear_ln(h, x, layer.linear2.weight, layer.linear2.bias, norm.weight, norm.bias, LN_EPS, dropout_p=p_drop)
+    return Fn.linear_ln(h, x, layer.linear2.weight, layer.linear2.bias, norm.weight, norm.bias, eps, dropout_p=p_drop)
 
 
 def encoder_layer_forward(layer, x, B, L, pos, key_mask):
     """Works for both this file's TransformerEncoderLayer and torch's nn.TransformerEncoderLayer holders."""
     p = layer_dropout_p(layer)
-    x = self_attention_block(layer.self_attn, layer.norm1, x, B, L, pos, key_mask, p)
-    return ffn_block(layer, layer.norm2, x, p)
+    x = self_attention_block(layer.self_attn, layer.norm1, x, B, L, pos, key_mask, p, eps=layer.norm1.eps)
+    return ffn_block(layer, layer.norm2, x, p, act=layer_activation(layer), eps=layer.norm2.eps)
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -207,5 +214,5 @@ class TransformerEncoderStack(nn.Module):
         for layer in encoder.layers:
             x = encoder_layer_forward(layer, x, B, L, None, km)
         if getattr(encoder, "norm", None) is not None:
-            x = Fn.layernorm(x, encoder.norm.weight, encoder.norm.bias, LN_EPS)
+            x = Fn.layernorm(x, encoder.norm.weight, encoder.norm.bias, encoder.norm.eps)
         return x

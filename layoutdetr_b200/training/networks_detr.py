@@ -40,8 +40,15 @@ def normalize_2nd_moment(x, eps=1e-8):
     return x * (x.square().mean(dim=1, keepdim=True) + eps).rsqrt()
 
 
-def build_backbone():
-    return _build_backbone()
+def build_backbone(kind="resnet50", background_size=256, hidden_dim=256):
+    """'resnet50': ResNet-50 + FrozenBN + sine position embedding (reference training/detr_backbone.py:98-115, what the reference
+    wires).  'vit_b16': the ViT-B/16 encoder of training/networks_vit.py behind the same interface."""
+    if kind == "resnet50":
+        return _build_backbone()
+    if kind == "vit_b16":
+        from .networks_vit import build_vit_backbone
+        return build_vit_backbone(background_size, background_size, hidden_dim)
+    raise ValueError("unknown backbone %r (resnet50 | vit_b16)" % (kind,))
 
 
 def init_tokenizer():
@@ -272,7 +279,7 @@ class Generator(nn.Module):
                  hidden_dim=256,
                  med_config='configs/med_config.json', bert_f_dim=768, bert_num_encoder_layers=12, bert_num_decoder_layers=12, bert_num_heads=12,
                  background_size=1024, im_f_dim=512,
-                 max_text_length=256):
+                 max_text_length=256, backbone='resnet50'):
         super().__init__()
         self.z_dim = z_dim
         self.num_bbox_labels = num_bbox_labels
@@ -284,7 +291,7 @@ class Generator(nn.Module):
         self.text_dedup = False      # reuse the frozen encoder's CLS features across calls on the same strings
         self._cls_cache = None
 
-        self.backbone = build_backbone()
+        self.backbone = build_backbone(backbone, background_size, hidden_dim)
         self.input_proj = nn.Conv2d(self.backbone.num_channels, hidden_dim, kernel_size=1)
 
         self.fc_z = nn.Linear(z_dim * 9, bert_f_dim)
@@ -383,7 +390,7 @@ class Discriminator(nn.Module):
                  hidden_dim=256,
                  med_config='configs/med_config.json', bert_f_dim=768, bert_num_encoder_layers=12, bert_num_decoder_layers=12, bert_num_heads=12,
                  background_size=1024, im_f_dim=512,
-                 max_text_length=256):
+                 max_text_length=256, backbone='resnet50'):
         super().__init__()
         from .networks_stylegan2 import Decoder
         self.num_bbox_labels = num_bbox_labels
@@ -394,7 +401,7 @@ class Discriminator(nn.Module):
         self.text_dedup = False
         self._cls_cache = None
 
-        self.backbone = build_backbone()
+        self.backbone = build_backbone(backbone, background_size, hidden_dim)
         self.input_proj = nn.Conv2d(self.backbone.num_channels, hidden_dim, kernel_size=1)
 
         self.fc_bbox = nn.Linear(4, bert_f_dim)

@@ -49,8 +49,9 @@ def load():
     class PatchEmbed(nn.Module):
         def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
             super().__init__()
+            hw = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
             self.proj = nn.Conv2d(in_chans, embed_dim, patch_size, patch_size)
-            self.num_patches = (img_size // patch_size) ** 2
+            self.num_patches = (hw[0] // patch_size) * (hw[1] // patch_size)
 
         def forward(self, x):
             return self.proj(x).flatten(2).transpose(1, 2)

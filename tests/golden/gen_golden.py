@@ -99,6 +99,26 @@ def gen_hungarian():
     print("hungarian goldens:", len(cases))
 
 
+def gen_vit():
+    """Reference `training/networks_vit.py: VisionTransformer.forward(x, mask)` (ViT-B/16 on nn.TransformerEncoder, :139-221) with
+    synthetic weights: a 64 x 96 image (4 x 6 patches, two of them masked out) and a 256 x 256 one (257 tokens)."""
+    import training.networks_vit as nv
+    out = {}
+    for name, (h, w), seed in (("small", (64, 96), 5), ("bg256", (256, 256), 6)):
+        torch.manual_seed(0)
+        m = nv.VisionTransformer(img_height=h, img_width=w).eval()
+        synth_state_dict(m)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn((2, 3, h, w), generator=g)
+        mask = torch.ones((2, 1, h, w))
+        mask[1, :, :16, 16:48] = 0                       # sample 1: patches (0, 1) and (0, 2) carry no image content
+        with torch.no_grad():
+            y = m(x, mask)
+        out[name] = dict(size=(h, w), seed=seed, y=y.clone(), y_nomask=m(x, torch.ones_like(mask)).detach().clone())
+    torch.save(out, os.path.join(GOLD, "vit_ref.pt"))
+    print("vit goldens:", {k: tuple(v["y"].shape) for k, v in out.items()})
+
+
 def gen_maxiou():
     """Reference `compute_maximum_iou` (metrics/metric_layoutnet.py:140-150, scipy + a multiprocessing pool) on two seeded sets of
     layouts whose label multisets repeat, incl. groups of different sizes on the two sides (the reshape(N, M) quirk)."""
@@ -340,6 +360,7 @@ def main():
     ap.add_argument("--only-ragged", action="store_true", help="regenerate tests/golden/model_b3_ragged.pt only")
     ap.add_argument("--only-dataset", action="store_true", help="regenerate tests/golden/tiny_layout.zip + dataset_ref.pt only")
     ap.add_argument("--only-maxiou", action="store_true", help="regenerate tests/golden/maxiou_ref.pt only")
+    ap.add_argument("--only-vit", action="store_true", help="regenerate tests/golden/vit_ref.pt only")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     nd = ref_shim.load()
@@ -350,6 +371,9 @@ def main():
     if args.only_maxiou:
         gen_maxiou()
         return
+    if args.only_vit:
+        gen_vit()
+        return
     if args.only_dataset:
         gen_dataset()
         gen_sampler()
@@ -357,6 +381,7 @@ def main():
     gen_ops()
     gen_hungarian()
     gen_maxiou()
+    gen_vit()
     gen_eval()
     gen_dataset()
     gen_sampler()

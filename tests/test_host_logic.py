@@ -141,15 +141,48 @@ def test_engine_refresh_stale_recomputes_in_place():
     import torch
     from layoutdetr_b200 import engine as E
     p = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
-    v = E.derived((p,), "twice", lambda: (p.detach() * 2).clone())
+    v = E.derived((p,), "twice", lambda t: (t.detach() * 2).clone())
     ptr = v.data_ptr()
     assert E.refresh_stale({id(p)}) == 0
     with torch.no_grad():
         p.add_(1.0)                       # bumps the version counter
     assert E.refresh_stale({id(object())}) == 0       # not ours: left alone
     assert E.refresh_stale({id(p)}) == 1
-    v2 = E.derived((p,), "twice", lambda: None)       # cache hit, no recompute
+    v2 = E.derived((p,), "twice", lambda t: None)     # cache hit, no recompute
     assert v2.data_ptr() == ptr and torch.equal(v2, (p.detach() * 2))
+
+
+def test_engine_tables_hold_no_strong_references():
+    """shadows die with their module (a training run deep-copies G_ema per snapshot / sweep), an entry is never served to
+    another object that re-uses the id(), and a managed (flat-storage) shadow follows torch-level in-place writes."""
+    import gc
+    import weakref
+    import torch
+    from layoutdetr_b200 import engine as E
+    lin = torch.nn.Linear(8, 4)
+    E.derived((lin.weight,), "probe", lambda t: t.detach() * 3)
+    E.derived((lin.weight, lin.bias), "pair", lambda w, b: torch.cat([w.detach().reshape(-1), b.detach()]))
+    n0 = len(E._shadow)
+    wref = weakref.ref(lin.weight)
+    del lin
+    gc.collect()
+    assert wref() is None and len(E._shadow) == n0 - 2
+    # same key, different object: treated as a miss
+    a = torch.nn.Parameter(torch.ones(2, 8))
+    key = ((id(a),), "k")
+    E.derived((a,), "k", lambda t: t.detach() + 1)
+    ent = E._shadow[key]
+    b = torch.nn.Parameter(torch.zeros(2, 8))
+    E._shadow[((id(b),), "k")] = ent                  # simulate a recycled id(): the entry of a dead object under b's key
+    assert torch.equal(E.derived((b,), "k", lambda t: t.detach() + 1), torch.ones(2, 8))
+    # managed shadow: refreshed when the parameter is written behind the optimizer kernel's back
+    p = torch.nn.Parameter(torch.arange(16.0).reshape(2, 8))
+    shadow = p.detach().to(torch.bfloat16).clone()
+    E.register_managed(p, shadow)
+    assert E._managed_shadow(p) is shadow
+    with torch.no_grad():
+        p.mul_(2.0)
+    assert torch.equal(E._managed_shadow(p).float(), p.detach()) and E._managed_shadow(p) is shadow
 
 
 def _eval_worker(rank, world, port, out):
