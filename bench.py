@@ -360,6 +360,7 @@ def run_ours(args):
 
     use_graph = bool(args.graph)
     gs = GraphedStep(trainer) if use_graph else None
+    graphed = gs is not None
     if gs is not None:
         gs.run(host_batches[0], zs[0], zs[1])               # warm-up + capture of the whole iteration
 
@@ -460,9 +461,11 @@ def run_ours(args):
     loop = None
     if args.loop_steps and world == 1:
         try:
-            del gs
+            gs.graphs.clear()                                    # release the captured graphs' memory pool
             torch.cuda.empty_cache()
-            loop = bench_loop(args, dev, B, world, rank)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):         # the loop prints the reference's progress lines; stdout carries ONE JSON line
+                loop = bench_loop(args, dev, B, world, rank)
         except Exception as e:                                   # never lose the headline line to the secondary measurement
             loop = dict(error="%s: %s" % (type(e).__name__, e))
 
@@ -485,7 +488,7 @@ def run_ours(args):
                                 text_dedup=bool(args.text_dedup), l2="flushed between timed steps (256 MiB write)",
                                 dropout=("on (train mode: DETR 0.1, BERT hidden / attention 0.1, in-kernel Philox)" if args.dropout
                                          else "off (modules in .eval(): deterministic kernels)"), parallelism="dp%d" % world,
-                                launch="cuda graph replay of the captured iteration" if gs is not None else "eager (one launch per kernel)",
+                                launch="cuda graph replay of the captured iteration" if graphed else "eager (one launch per kernel)",
                                 lanes=dict(level=LANES.level, text_ctas=LANES.text_ctas, lm_ctas=LANES.lm_ctas, priority=LANES.high_priority,
                                            note="independent sub-graphs of the iteration on parallel streams (same kernels, same operands)")),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),

@@ -173,8 +173,7 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     Cout, Cin_w, KH, KW = weight.shape
     assert Cin_w == Cin
     g = _Geom(B, Cin, H, W, Cout, KH, KW, s, p, K.conv_out_size(H, KH, s, p), K.conv_out_size(W, KW, s, p))
-    w = weight.detach() if weight_gradients_disabled else weight
-    y = _Conv.apply(input, w, g)
+    y = _Conv.apply(input, weight, g)
     return y if bias is None else y + bias.to(y.dtype).reshape(1, -1, 1, 1)
 
 
@@ -188,6 +187,5 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
     H, W = (Ho - 1) * s - 2 * p + KH + op, (Wo - 1) * s - 2 * p + KW + op
     g = _Geom(B, Cx, H, W, Cy, KH, KW, s, p, Ho, Wo)
     assert K.conv_out_size(H, KH, s, p) == Ho and K.conv_out_size(W, KW, s, p) == Wo
-    w = weight.detach() if weight_gradients_disabled else weight
-    x = _ConvT.apply(input, w, g)
+    x = _ConvT.apply(input, weight, g)
     return x if bias is None else x + bias.to(x.dtype).reshape(1, -1, 1, 1)

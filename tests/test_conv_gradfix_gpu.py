@@ -43,11 +43,22 @@ def test_conv_values_first_and_second_order(k, stride, pad, cin, cout, transpose
 
 
 def test_no_weight_gradients_context():
+    """`no_weight_gradients()` (reference torch_utils/ops/conv2d_gradfix.py:37-42, used by R1 in training/loss.py:209-215):
+    backward passes executed INSIDE the context skip the first-order weight gradient; the penalty's own backward, outside
+    the context, still reaches the weights through the second-order terms."""
     from layoutdetr_b200.torch_utils.ops import conv2d_gradfix as cg
     x = torch.randn((1, 8, 8, 8), device="cuda", requires_grad=True)
     w = torch.randn((8, 8, 3, 3), device="cuda", requires_grad=True)
+    y = cg.conv2d(x, w, padding=1)
     with cg.no_weight_gradients():
-        y = cg.conv2d(x, w, padding=1)
-        gx, = torch.autograd.grad(y.sum(), x, create_graph=True)
+        gx, gw = torch.autograd.grad(y.square().sum(), [x, w], create_graph=True, allow_unused=True)
+    assert gw is None and gx is not None
     gx.square().sum().backward()
-    assert w.grad is None and x.grad is not None
+    assert w.grad is not None and x.grad is not None
+    # against torch's own double backward of the same expression (bf16 tensor-core contraction: loose tolerance)
+    x2, w2 = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    y2 = torch.nn.functional.conv2d(x2, w2, padding=1)
+    gx2, = torch.autograd.grad(y2.square().sum(), [x2], create_graph=True)
+    gx2.square().sum().backward()
+    for a, b in ((x.grad, x2.grad), (w.grad, w2.grad)):
+        assert float((a - b).norm() / b.norm()) < 5e-2

@@ -1,2 +1,2 @@
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout=600 > gpurun_out/r2_pytest_gpu_a.log 2>&1; tail -25 gpurun_out/r2_pytest_gpu_a.log
-timeout 400 python bench.py --variants 0 > gpurun_out/r2_bench_b.json 2> gpurun_out/r2_bench_b.err; tail -c 900 gpurun_out/r2_bench_b.json; tail -5 gpurun_out/r2_bench_b.err
+timeout 900 python -m pytest tests/test_conv_gradfix_gpu.py tests/test_graph_gpu.py tests/test_lanes_gpu.py -m gpu -q --timeout=600 > gpurun_out/r2_pytest_gpu_b.log 2>&1; tail -12 gpurun_out/r2_pytest_gpu_b.log
+timeout 600 python bench.py > gpurun_out/r2_bench_a.json 2> gpurun_out/r2_bench_a.err; tail -c 2500 gpurun_out/r2_bench_a.json; tail -5 gpurun_out/r2_bench_a.err
