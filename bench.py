@@ -293,6 +293,7 @@ def run_loop(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
     B = args.batch if args.scaling == "weak" else args.batch // world
@@ -322,6 +323,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")      # peer traffic over NVLink / NVSwitch only (north star: "NVLink only")
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()        # fail loudly if the CUDA library is missing
     pk = peaks()
@@ -433,6 +435,22 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = B * world / float(te.item())
 
+    # ---- data-parallel replicas must hold bit-identical weights after the run (reference check_ddp_consistency,
+    # torch_utils/misc.py:183): a 64-bit wrap-around sum of the fp32 bit patterns of G / D / G_ema, gathered from every rank
+    replicas = None
+    if world > 1:
+        sums = torch.stack([f.p.view(torch.int32).to(torch.int64).sum() for f in (trainer.flat["G"], trainer.flat["D"], trainer.flat_ema)])
+        allsums = [torch.zeros_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        replicas = dict(identical=bool(all(torch.equal(allsums[0], a) for a in allsums)), checksum_G_D_Gema=[int(v) for v in allsums[0].tolist()],
+                        check="int64 sum of the fp32 bit patterns of every trainable parameter, all ranks")
+    exchange = None
+    if world > 1 and graphed:
+        exchange = dict(next(reversed(gs.graphs.values())).get("exchange") or {},
+                        bucket_mb=float(os.environ.get("LD_DP_BUCKET_MB", "32")), overlap=os.environ.get("LD_DP_OVERLAP", "1") != "0",
+                        note="buckets of the flat fp32 gradient buffer all-reduced on a communication stream from inside the backward pass "
+                             "(early) / after it (late); NCCL kernels captured into the iteration's CUDA graph")
+
     # ---- exact work-saving variant (reported separately, never as the headline): frozen text-encoder features computed
     # once per iteration per network instead of 2x / 3x, and all-padding token columns dropped (bit-identical results)
     variant = None
@@ -492,7 +510,8 @@ def run_ours(args):
                                 lanes=dict(level=LANES.level, text_ctas=LANES.text_ctas, lm_ctas=LANES.lm_ctas, priority=LANES.high_priority,
                                            note="independent sub-graphs of the iteration on parallel streams (same kernels, same operands)")),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, variants=[variant] if variant else [], loop=loop)
+                    gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, variants=[variant] if variant else [], loop=loop,
+                    replicas=replicas, exchange=exchange)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

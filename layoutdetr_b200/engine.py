@@ -203,13 +203,40 @@ def derived(param_tuple, tag, fn):
     return v
 
 
+_grad_watch = {}        # id(param) -> (GradExchange, bucket): parameters whose gradient writes are reported (data-parallel runs only)
+_grad_pending = []      # writes handed out by grad_buffer since the last grad_writes_done()
+
+
 def grad_buffer(param):
     """fp32 gradient accumulator of a parameter (created zeroed on first use).  Backward kernels add
     straight into it (GEMM epilogue accumulate / atomics) instead of materialising a temporary that
     autograd would add afterwards."""
     if param.grad is None:
         param.grad = torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format)
+    if _grad_watch:
+        ent = _grad_watch.get(id(param))
+        if ent is not None:
+            _grad_pending.append(ent)
     return param.grad
+
+
+def watch_grad(param, exchange, bucket):
+    _grad_watch[id(param)] = (exchange, bucket)
+
+
+def unwatch_grads(exchange):
+    for k in [k for k, v in _grad_watch.items() if v[0] is exchange]:
+        del _grad_watch[k]
+
+
+def grad_writes_done():
+    """Called at the end of every hand-written backward node (functional._Fn): the kernels that write the buffers handed out
+    by grad_buffer since the last call have been issued on the current stream (exchange.GradExchange)."""
+    if _grad_pending:
+        pend = list(_grad_pending)
+        _grad_pending.clear()
+        for ex, b in pend:
+            ex.written(b)
 
 
 def wgrad_split_k(M_out, N_out, K_red):

@@ -11,7 +11,8 @@ How "last write" is known: gradient writes happen in two ways — (a) the hand-w
 backward node through engine.grad_writes_done), (b) torch's own AccumulateGrad for the few parameters that reach plain torch
 ops (post-accumulate-grad hooks).  A first iteration in TRACE mode counts the writes per bucket; armed with those counts the
 next iterations launch a bucket when its count is reached.  The number of writes is a property of the code path (shapes,
-flags), not of the data; a write that arrives after its bucket was launched, or a bucket that never fills, raises.
+flags), not of the data; a write that arrives after its bucket was launched raises, a bucket that never fills is exchanged
+in finish().
 
 Stream rules: every write records an event on the stream it was issued on (lanes.py runs backward nodes on several streams);
 the communication stream waits for the newest event of every stream that wrote into the bucket.  finish() makes the current
@@ -135,25 +136,24 @@ class GradExchange:
             raise RuntimeError("gradient exchange %s: finish() without begin()" % self.name)
         E.grad_writes_done()
         counts = list(self.counts)
-        if self.expected is not None:
-            short = [b for b in range(len(self.bounds)) if not self.launched[b] and self.expected[b] > 0]
-            if short:
-                raise RuntimeError("gradient exchange %s: buckets %s saw fewer writes than traced (%s < %s)" % (
-                    self.name, short, [counts[b] for b in short], [self.expected[b] for b in short]))
         self.open = False
         left = [b for b in range(len(self.bounds)) if not self.launched[b]]
-        if left:
-            if len(left) == len(self.bounds):
-                # nothing went early (trace iteration / overlap off): one exchange of the whole buffer, as the reference's
-                self.launched = [True] * len(self.bounds)
-                self.stats["late"] += len(left)
-                if self.cuda:
-                    torch.distributed.all_reduce(self.g, group=self.group)
-                else:
-                    torch.distributed.all_reduce(self.g, group=self.group)
-                return counts
-            for b in left:
-                self._launch(b, early=False)
+        if len(left) == len(self.bounds):
+            # nothing went early (trace iteration / overlap off): one exchange of the whole buffer on the current stream, the
+            # reference's order
+            self.reduce_all()
+            return counts
+        for b in left:                  # fewer writes than traced (cannot corrupt anything): exchanged now
+            self._launch(b, early=False)
         if self.cuda and self.comm is not None:
             torch.cuda.current_stream(self.g.device).wait_stream(self.comm)
         return counts
+
+    def reduce_all(self):
+        """Plain exchange of the whole buffer on the current stream (also the replay-time call of the segmented schedule)."""
+        if self.world <= 1:
+            return
+        self.open = False
+        self.launched = [True] * len(self.bounds)
+        self.stats["late"] += len(self.bounds)
+        torch.distributed.all_reduce(self.g, group=self.group)

@@ -35,6 +35,21 @@ class _Fn(torch.autograd.Function):
         _TRACK[0] = torch.is_grad_enabled()
         return super().apply(*args)
 
+    def __init_subclass__(cls, **kw):
+        # every backward node reports the end of its gradient-buffer writes (engine.grad_writes_done: no-op unless a
+        # data-parallel gradient exchange watches the parameters)
+        super().__init_subclass__(**kw)
+        bw = cls.__dict__.get("backward")
+        if isinstance(bw, staticmethod):
+            inner = bw.__func__
+
+            def backward(ctx, *grads):
+                out = inner(ctx, *grads)
+                E.grad_writes_done()
+                return out
+            backward.__doc__ = inner.__doc__
+            cls.backward = staticmethod(backward)
+
 
 def _need(ctx):
     return _TRACK[0] and any(ctx.needs_input_grad)

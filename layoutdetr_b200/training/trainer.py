@@ -19,6 +19,7 @@ import torch
 
 from .. import engine as E
 from .. import rng as RNG
+from ..exchange import GradExchange
 from ..flat import FlatParams
 from ..lanes import LANES
 from . import networks_detr as nd
@@ -55,6 +56,13 @@ class Trainer:
         self._suspending = False
         self._param_ids = None
         self.segmented = False               # True: _phase_grads("G") ends a CUDA-graph segment (multi-GPU, NCCL between graphs)
+        # data-parallel gradient exchange (exchange.py): per network, buckets of the flat gradient buffer all-reduced on a
+        # communication stream while the backward pass is still running.  `_expected` (per-bucket write counts of one backward
+        # pass) is only set by GraphedStep around a capture, from the counts traced in its warm-up iterations of the SAME
+        # batch key; eager iterations always trace (one all-reduce after the backward pass, the reference's order).
+        self.exch = {n: GradExchange(f.g, f.params, f.offsets, group=process_group, world=num_gpus, name=n) for n, f in self.flat.items()}
+        self._expected = {}
+        self._traced = {}
 
     def _phase(self, name, batch, gen_z):
         self._phase_grads(name, batch, gen_z)
@@ -63,7 +71,7 @@ class Trainer:
 
     def _phase_reduce(self, name):
         if self.num_gpus > 1:
-            torch.distributed.all_reduce(self.flat[name].g, group=self.pg)
+            self._traced[name] = self.exch[name].finish()
 
     def _phase_step(self, name):
         o = self.opt[name]
@@ -84,6 +92,7 @@ class Trainer:
         split = name == "D" and self._real_issued                   # the real-sample half already ran on the R lane
         if not split:
             self.flat[name].zero_grad()
+            self.exch[name].begin(self._expected.get(name))
         mod.requires_grad_(True)
         mod.text_encoder.requires_grad_(False)
         if split:
@@ -134,6 +143,7 @@ class Trainer:
                 D.requires_grad_(True)
                 D.text_encoder.requires_grad_(False)
                 self.flat["D"].zero_grad()
+                self.exch["D"].begin(self._expected.get("D"))
                 self._accumulate("Dreal", batch, None)
                 D.requires_grad_(False)
                 LANES.join_children()
@@ -195,6 +205,7 @@ class Trainer:
             for name, zs in (("G", zs_g), ("D", zs_d)):
                 mod = self.G if name == "G" else self.D
                 self.flat[name].zero_grad()
+                self.exch[name].begin(None)
                 mod.requires_grad_(True)
                 mod.text_encoder.requires_grad_(False)
                 for batch, z in zip(batches, zs):
@@ -306,8 +317,8 @@ class GraphedStep:
         if len(gr) == 1:
             gr[0].replay()
         else:
-            gr[0].replay(); tr._phase_reduce("G")
-            gr[1].replay(); tr._phase_reduce("D")
+            gr[0].replay(); tr.exch["G"].reduce_all()
+            gr[1].replay(); tr.exch["D"].reduce_all()
             gr[2].replay()
         tr.update_ema()                                          # EMA beta depends on the image counter: kept out of the graph
 
@@ -349,31 +360,43 @@ class GraphedStep:
                     tr.iteration(st, st["z_g"], st["z_d"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            tr.segmented = tr.num_gpus > 1
             from .. import _lib
             n0 = _lib.launch_count()
-            if tr.num_gpus == 1:
+            overlap = tr.num_gpus > 1 and tr.exch["G"].overlap
+            tr.segmented = tr.num_gpus > 1 and not overlap
+            if not tr.segmented:
+                # one graph for the whole iteration.  With N > 1 the bucketed NCCL all-reduces are captured too, on the
+                # communication stream, launched from inside the backward pass (exchange.py); the write counts that tell a
+                # bucket it is complete were traced by the warm-up iterations above
+                if overlap:
+                    tr._expected = {n: list(c) for n, c in tr._traced.items() if c is not None}
                 segs = [lambda: tr.iteration(st, st["z_g"], st["z_d"], update_ema=False)]
             else:
-                # NCCL collectives stay outside the graphs: [Gmain grads] -AR- [Adam(G) + Dmain grads] -AR- [Adam(D)]
+                # LD_DP_OVERLAP=0: NCCL collectives stay outside the graphs: [Gmain grads] -AR- [Adam(G) + Dmain grads] -AR- [Adam(D)]
                 segs = [lambda: tr._phase_grads("G", st, st["z_g"]),
                         lambda: (tr._phase_step("G"), tr._phase_grads("D", st, st["z_d"])),
                         lambda: tr._phase_step("D")]
             graphs, pool = [], None
-            for i, seg in enumerate(segs):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=side):
-                    seg()
-                pool = g.pool()
-                graphs.append(g)
-                if tr.num_gpus > 1 and i < len(segs) - 1:       # keep the eager state consistent between captures
-                    torch.cuda.synchronize()
+            for x in tr.exch.values():
+                x.stats = dict(early=0, late=0)
+            try:
+                for i, seg in enumerate(segs):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool, stream=side, capture_error_mode="thread_local" if tr.num_gpus > 1 else "global"):
+                        seg()
+                    pool = g.pool()
+                    graphs.append(g)
+                    if tr.segmented and i < len(segs) - 1:       # keep the eager state consistent between captures
+                        torch.cuda.synchronize()
+            finally:
+                tr._expected = {}
             out = {ph: {k: v for k, v in terms.items()} for ph, terms in tr.loss.last.items()}
             tr.segmented = False
             # host-derived device tensors the captured kernels read (valid-slot indices): owned by the entry, so the module-level
             # caches in networks_detr may be recycled without pulling memory from under a graph
             keep = [nd.valid_index(st["padding_mask"])]
-            ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0, keep=keep)
+            ent = dict(graphs=graphs, static=st, out=out, launches=_lib.launch_count() - n0, keep=keep,
+                       exchange={n: dict(buckets=len(x.bounds), early=x.stats["early"], late=x.stats["late"]) for n, x in tr.exch.items()})
             self.graphs[key] = ent
             self._restore(snap, st)
             self._replay(ent)                                    # the first real step on this batch

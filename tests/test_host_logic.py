@@ -268,3 +268,111 @@ def test_box_loss_arithmetic_edge_cases_match_oracle_autograd():
     lib.host_giou_loss(P(f), P(r), ctypes.c_long(6), P(lo), P(jf))
     torch.testing.assert_close(lo[0], ref.detach(), atol=1e-6, rtol=1e-5)
     torch.testing.assert_close(jf, fr.grad, atol=1e-6, rtol=1e-4)
+
+
+def _exchange_worker(rank, world, port, out):
+    """Two ranks (gloo, CPU): a toy network whose gradients reach the flat buffer through BOTH write paths of the product —
+    torch's AccumulateGrad (post-accumulate hooks) and a hand-written `_Fn` backward adding straight into engine.grad_buffer —
+    exchanged by exchange.GradExchange: one trace pass, then passes armed with the traced counts."""
+    import torch.distributed as dist
+    from layoutdetr_b200 import engine as E
+    from layoutdetr_b200 import functional as Fn
+    from layoutdetr_b200.exchange import GradExchange
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class DirectLinear(Fn._Fn):                      # weight gradient written in place, None returned to autograd (functional.py convention)
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.w = w
+            ctx.save_for_backward(x)
+            return x @ w.detach().t()
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, = ctx.saved_tensors
+            E.grad_buffer(ctx.w).add_(dy.t() @ x)
+            return dy @ ctx.w.detach(), None
+
+    torch.manual_seed(0)
+    shapes = [(8, 8)] * 6 + [(8,)] * 3
+    params = [torch.nn.Parameter(torch.randn(s) * 0.3) for s in shapes]
+    offs, total = [], 0
+    for p in params:
+        offs.append(total)
+        total += (p.numel() + 7) // 8 * 8
+    g = torch.zeros(total)
+    for p, o in zip(params, offs):
+        p.grad = g[o:o + p.numel()].view(p.shape)
+    ex = GradExchange(g, params, offs, world=world, bucket_mb=128 * 4 / (1 << 20), overlap=True, name="toy")   # 128 floats per bucket
+    nb = len(ex.bounds)
+
+    def backward_pass(x, skip_last=False):
+        h = x
+        for i in range(6):
+            w = params[i]
+            h = DirectLinear.apply(h, w) if i % 2 == 0 else h @ w.t()          # in-place path / AccumulateGrad path
+            if i < 3:
+                h = h + params[6 + i]
+            h = torch.tanh(h)
+        if not skip_last:
+            h = DirectLinear.apply(h, params[0])                               # weight 0 is used twice: two writes into its bucket
+        h.sum().backward()
+
+    def local_grads(x):
+        g.zero_()
+        backward_pass(x)
+        return g.clone()
+
+    results = []
+    xs = [torch.randn(4, 8, generator=torch.Generator().manual_seed(10 * it + rank)) for it in range(3)]
+    expected = None
+    for it in range(3):
+        mine = local_grads(xs[it])
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        g.zero_()
+        ex.begin(expected)
+        backward_pass(xs[it])
+        counts = ex.finish()
+        results.append(bool(torch.allclose(g, sum(gathered), atol=1e-6)))
+        if it == 0:
+            assert ex.stats["early"] == 0                  # the trace pass exchanges after the backward pass
+            expected = counts
+    early = ex.stats["early"]
+    # a pass with FEWER writes than traced: nothing is lost (late exchange); a write AFTER a bucket went out must raise
+    g.zero_()
+    ex.begin(expected)
+    backward_pass(xs[0], skip_last=True)
+    ex.finish()
+    g.zero_()
+    ex.begin([max(0, c - 1) if i == ex.bucket_of[id(params[0])] else c for i, c in enumerate(expected)])
+    raised = False
+    try:
+        backward_pass(xs[0])
+    except RuntimeError as e:
+        raised = "after its all-reduce" in str(e)
+    if not raised:
+        ex.finish()
+    ex.close()
+    if rank == 0:
+        out.put((results, nb, early, raised))
+    dist.barrier() if raised is False else None
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, 29653, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results, nb, early, raised = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    assert nb >= 3, nb
+    assert results == [True, True, True], results
+    assert early == 2 * nb, (early, nb)              # both armed passes sent every bucket from inside the backward pass
+    assert raised
