@@ -251,34 +251,49 @@ def run_eval(args):
 
 # --------------------------------------------------------------------------------------------------------
 def gemm_roofline(torch, K, pk):
-    """Dominant kernel (gemm_bf16_kernel) on the dominant shape — the BERT FFN GEMM of one text-encoder call at bs16:
-    M = 16*9*256 tokens, N = 3072, K = 768 — timed alone with CUDA events on the launching stream."""
+    """Dominant kernel (gemm_bf16_2sm_kernel) on the dominant shape — the BERT FFN GEMM of one text-encoder call at bs16:
+    M = 16*9*256 tokens, N = 3072, K = 768 — timed alone with CUDA events on the launching stream, AS THE STEP RUNS IT (bias + GELU
+    epilogue, bf16 out: 60 of the 68 BERT-layer executions per iteration); the plain epilogue (no bias, no activation) is reported as
+    a sub-field."""
     M, N, Kd = 16 * 9 * 256, 3072, 768
     a = torch.randn((M, Kd), device="cuda").to(torch.bfloat16)
     w = torch.randn((N, Kd), device="cuda").to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
     out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        K.linear(a, w, out=out)
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        K.linear(a, w, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[len(ts) // 2]
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    ms = timed(lambda: K.linear(a, w, bias, act=K.ACT_GELU, out=out))
+    ms_plain = timed(lambda: K.linear(a, w, out=out))
     flops = 2.0 * M * N * Kd
     ach = flops / (ms * 1e-3) / 1e12
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape from the ncu --set full capture in
-    # profiles/r1_gemm_ncu_full_epilogue_variants.txt (61.5 MB read + 174.3 MB written; algorithmic: 61.3 + 226.5 MB, part of the
-    # output still sits in L2 when the kernel ends)
+    ach_plain = flops / (ms_plain * 1e-3) / 1e12
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture named in traffic_note
+    # (algorithmic: 61.3 MB of operands + 226.5 MB of output; part of the output still sits in L2 when the kernel ends)
     two_sm = os.environ.get("LD_GEMM_2SM", "1") != "0"      # this shape has 1728 pair tiles: the cta_group::2 kernel unless disabled
-    return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=235.7e6,
-                traffic_note="ncu --set full capture of the single-CTA kernel on this shape (profiles/r1_gemm_ncu_full_epilogue_variants.txt)",
-                kernel="gemm_bf16_2sm_kernel (cta_group::2)" if two_sm else "gemm_bf16_kernel", shape=[M, N, Kd], ms=ms,
+    traffic, note = 235.7e6, "ncu --set full capture of the single-CTA kernel on this shape (profiles/r1_gemm_ncu_full_epilogue_variants.txt)"
+    tp = os.path.join(ROOT, "profiles", "r2_gemm_2sm_ncu_traffic.json")
+    if two_sm and os.path.exists(tp):
+        with open(tp) as f:
+            d = json.load(f)
+        traffic, note = d["traffic_bytes"], d["note"]
+    return dict(bound="tensor", achieved=ach, peak=pk["burst"], unit="TFLOP/s", frac=ach / pk["burst"], traffic=traffic,
+                traffic_note=note, kernel="gemm_bf16_2sm_kernel (cta_group::2)" if two_sm else "gemm_bf16_kernel", shape=[M, N, Kd], ms=ms,
+                epilogue="bias + GELU, bf16 out (as the step runs it)",
+                plain_epilogue=dict(achieved=ach_plain, frac=ach_plain / pk["burst"], ms=ms_plain, note="same shape, no bias / activation"),
                 peak_source=pk["src"] + " burst (kernel timed alone)")
 
 

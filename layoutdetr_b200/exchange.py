@@ -69,7 +69,10 @@ class GradExchange:
             E.watch_grad(p, self, self.bucket_of[id(p)])
             if hasattr(p, "register_post_accumulate_grad_hook") and p.is_leaf:
                 b = self.bucket_of[id(p)]
+                rg = p.requires_grad                  # the Trainer keeps parameters frozen between phases; hooks need the flag on
+                p.requires_grad_(True)
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, b=b: self.written(b)))
+                p.requires_grad_(rg)
 
     def close(self):
         for h in self._hooks:

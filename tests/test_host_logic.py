@@ -305,10 +305,13 @@ def _exchange_worker(rank, world, port, out):
     g = torch.zeros(total)
     for p, o in zip(params, offs):
         p.grad = g[o:o + p.numel()].view(p.shape)
+        p.requires_grad_(False)                     # as the Trainer leaves them between phases
     ex = GradExchange(g, params, offs, world=world, bucket_mb=128 * 4 / (1 << 20), overlap=True, name="toy")   # 128 floats per bucket
     nb = len(ex.bounds)
 
     def backward_pass(x, skip_last=False):
+        for p in params:
+            p.requires_grad_(True)
         h = x
         for i in range(6):
             w = params[i]
