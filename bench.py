@@ -529,6 +529,9 @@ def run_ours(args):
                     replicas=replicas, exchange=exchange)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if gs is not None:
+            gs.close()              # captured NCCL collectives must be released before the communicator goes away
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -93,6 +93,35 @@ __device__ __forceinline__ float gelu_erf(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));      // t >= 2: no range fix-up needed
     return fmaxf(x, 0.0f) - fabsf(x * r);
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE-rn results — same roundings as the scalar ops).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t f2_splat(float c) { return f2_pack(c, c); }
+
+// gelu_erf on two values at once: the same operations in the same order as the scalar version (bit-identical results),
+// with the polynomial, the four squarings and the final products issued as FFMA2 / FMUL2.
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+    const f32x2_t ax = f2_pack(fabsf(x0), fabsf(x1));
+    f32x2_t t = f2_fma(f2_splat(5.6212996640e-06f), ax, f2_splat(5.1055209009e-05f));
+    t = f2_fma(t, ax, f2_splat(3.9686137011e-05f));
+    t = f2_fma(t, ax, f2_splat(3.4227392389e-03f));
+    t = f2_fma(t, ax, f2_splat(2.2076998457e-02f));
+    t = f2_fma(t, ax, f2_splat(5.2075163037e-02f));
+    t = f2_fma(t, ax, f2_splat(1.0442737824e+00f));
+    t = f2_mul(t, t); t = f2_mul(t, t); t = f2_mul(t, t); t = f2_mul(t, t);
+    float t0, t1, r0, r1;
+    f2_unpack(t, t0, t1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+    // relu(x) - |x| r  ==  fma(|x| r, -1, relu(x)): one rounding of the product, exact negation, one rounding of the sum
+    const f32x2_t q = f2_mul(ax, f2_pack(r0, r1));
+    const f32x2_t o = f2_fma(q, f2_splat(-1.0f), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+    f2_unpack(o, x0, x1);
+}
+
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);

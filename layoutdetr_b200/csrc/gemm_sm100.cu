@@ -223,10 +223,11 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
     for (int j = 0; j < 8; ++j) {
         const float4 s4 = lds_f4(cs_a + (c0 + 4 * j) * 4);
         const float4 b4 = lds_f4(cb_a + (c0 + 4 * j) * 4);
-        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), s4.x, b4.x);
-        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
-        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z);
-        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
+        // acc * scale + bias as two FFMA2 (same roundings as four FFMA, half the issue slots)
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), f2_pack(s4.x, s4.y), f2_pack(b4.x, b4.y)),
+                  v[4 * j + 0], v[4 * j + 1]);
+        f2_unpack(f2_fma(f2_pack(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), f2_pack(s4.z, s4.w), f2_pack(b4.z, b4.w)),
+                  v[4 * j + 2], v[4 * j + 3]);
     }
     if (RES == 1 && r_off >= 0) {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + r_off + n_base);
@@ -249,7 +250,10 @@ __device__ __forceinline__ void epilogue_fast_chunk(const KParams& p, const uint
             v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
         }
     }
-    if (ACT != LD_ACT_NONE) {
+    if (ACT == LD_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) gelu_erf_x2(v[i], v[i + 1]);      // FFMA2 / FMUL2: the epilogue is issue-bound here
+    } else if (ACT != LD_ACT_NONE) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = act_ct<ACT>(v[i]);
     }

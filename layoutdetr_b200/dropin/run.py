@@ -19,6 +19,7 @@ def main():
         script = os.path.join(ref, script)
     sys.argv = [script] + sys.argv[2:]
     sys.path[:0] = [overlay, ref]
+    os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")      # data-parallel workers (train.py spawns them): peer traffic over NVLink only
     os.chdir(ref)                       # the reference opens configs/med_config.json and pretrained/ by relative path
     runpy.run_path(script, run_name="__main__")
 

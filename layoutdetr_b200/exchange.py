@@ -28,6 +28,9 @@ import torch
 from . import engine as E
 
 
+_COMM_STREAMS = {}
+
+
 class GradExchange:
     def __init__(self, g, params, offsets, group=None, world=1, bucket_mb=None, overlap=None, name=""):
         self.g = g
@@ -95,7 +98,12 @@ class GradExchange:
         self.events = [dict() for _ in range(nb)]
         self.open = True
         if self.cuda and self.comm is None:
-            self.comm = torch.cuda.Stream(device=self.g.device, priority=-1)
+            # ONE communication stream per device for every exchange (G and D buckets interleave while the real-sample lane
+            # runs next to Gmain): collectives of one communicator stay in one stream order on every rank
+            key = self.g.device.index
+            if key not in _COMM_STREAMS:
+                _COMM_STREAMS[key] = torch.cuda.Stream(device=self.g.device, priority=-1)
+            self.comm = _COMM_STREAMS[key]
 
     def written(self, b):
         """One write into bucket `b` has been issued on the current stream."""

@@ -322,6 +322,17 @@ class GraphedStep:
             gr[2].replay()
         tr.update_ema()                                          # EMA beta depends on the image counter: kept out of the graph
 
+    def close(self):
+        """Drop every captured graph (and its memory pool).  With N > 1 the graphs hold captured NCCL collectives: the communicator
+        cannot be destroyed while they are alive (ncclCommDestroy waits for its graph-captured operations to be released), so
+        call this before torch.distributed.destroy_process_group()."""
+        import gc
+        for ent in self.graphs.values():
+            ent.clear()
+        self.graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+
     def run_static(self):
         """Replay the captured iteration on whatever the static input buffers currently hold (inputs resident in HBM)."""
         ent = next(reversed(self.graphs.values()))               # most recently used graph

@@ -393,6 +393,8 @@ def training_loop(
 
     if stats_jsonl is not None:
         stats_jsonl.close()
+    if graphed is not None and num_gpus > 1:
+        graphed.close()              # graphs holding captured NCCL collectives must be gone before the process group is torn down
     if rank == 0:
         print()
         print('Exiting...')

@@ -267,7 +267,7 @@ def gen_dataset():
     print("dataset goldens:", out["len"], "samples, patch_shape", out["patch_shape"])
 
 
-def run_model_goldens(nd, G, D, name, batch, n_valid, seed, ragged=None):
+def run_model_goldens(nd, G, D, name, batch, n_valid, seed, ragged=None, light=False):
     inp = make_inputs(batch, n_valid=n_valid, seed=seed) if ragged is None else make_ragged_inputs(ragged, seed=seed)
     store = {}
     hooks = [_hook_outputs(G.text_encoder, store, "G.text_encoder"), _hook_outputs(G.input_proj, store, "G.input_proj"),
@@ -298,10 +298,12 @@ def run_model_goldens(nd, G, D, name, batch, n_valid, seed, ragged=None):
                  "bbox_pred_uncond", "logit_cls_uncond"]
         d = dict(zip(names, [r.clone() for r in dres]))
         bg = d.pop("bg_rec")
-        d["bg_rec_sub"] = bg[:, :, ::8, ::8].clone()
+        d["bg_rec_sub"] = bg[:, :, ::8, ::8].clone() if not light else bg[:, :, ::16, ::16].to(torch.float16)
         d["bg_rec_mean"] = float(bg.mean())
         d["bg_rec_std"] = float(bg.std())
         out["D"] = d
+        if light:                        # the benched batch size: outputs only (file size)
+            out["G_inter"] = {"text_cls": out["G_inter"]["text_cls"].to(torch.float16), "hs": out["G_inter"]["hs"]}
         fres = D(out["G"]["bbox_fake"], inp["bbox_class"], inp["bbox_text"], inp["bbox_patch"], inp["padding_mask"],
                  inp["background"], inp["c"])
         out["D_fake"] = dict(logit_disc=fres[0].clone(), logit_disc_uncond=fres[1].clone())
@@ -320,7 +322,7 @@ def run_generator_1024(nd, G, name="model_b1_bg1024", seed=21):
     print("saved", name)
 
 
-def run_loss_goldens(nd, G, D, name, batch, n_valid, seed):
+def run_loss_goldens(nd, G, D, name, batch, n_valid, seed, small_limit=4096):
     """Full reference loss + backward (training/loss.py accumulate_gradients) with dropout off."""
     import training.loss as ref_loss
     from torch_utils import training_stats
@@ -345,7 +347,7 @@ def run_loss_goldens(nd, G, D, name, batch, n_valid, seed):
             if p.grad is None:
                 continue
             norms[k] = float(p.grad.norm())
-            if p.grad.numel() <= 4096:
+            if p.grad.numel() <= small_limit:
                 small[k] = p.grad.clone()
         out["grads"][phase] = dict(norms=norms, small=small)
     torch.save(out, os.path.join(GOLD, name + ".pt"))
@@ -361,6 +363,7 @@ def main():
     ap.add_argument("--only-dataset", action="store_true", help="regenerate tests/golden/tiny_layout.zip + dataset_ref.pt only")
     ap.add_argument("--only-maxiou", action="store_true", help="regenerate tests/golden/maxiou_ref.pt only")
     ap.add_argument("--only-vit", action="store_true", help="regenerate tests/golden/vit_ref.pt only")
+    ap.add_argument("--only-bs16", action="store_true", help="model_b16_v8.pt + loss_b16_v8.pt only: the benched batch size (BASELINE configs[1])")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     nd = ref_shim.load()
@@ -392,6 +395,10 @@ def main():
     D = nd.Discriminator(**ref_shim.D_KWARGS).eval()
     synth_state_dict(G)
     synth_state_dict(D)
+    if args.only_bs16:
+        run_model_goldens(nd, G, D, "model_b16_v8", batch=16, n_valid=8, seed=16, light=True)
+        run_loss_goldens(nd, G, D, "loss_b16_v8", batch=16, n_valid=8, seed=16, small_limit=1024)
+        return
     if args.only_ragged:
         run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
         run_generator_1024(nd, G)
@@ -404,8 +411,10 @@ def main():
     run_model_goldens(nd, G, D, "model_b2_v8", batch=2, n_valid=8, seed=2)
     run_model_goldens(nd, G, D, "model_b3_ragged", batch=3, n_valid=9, seed=13, ragged=[1, 5, 9])
     run_generator_1024(nd, G)
+    run_model_goldens(nd, G, D, "model_b16_v8", batch=16, n_valid=8, seed=16, light=True)
     if not args.skip_loss:
         run_loss_goldens(nd, G, D, "loss_b2_v8", batch=2, n_valid=8, seed=2)
+        run_loss_goldens(nd, G, D, "loss_b16_v8", batch=16, n_valid=8, seed=16, small_limit=1024)
 
 
 if __name__ == "__main__":

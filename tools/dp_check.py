@@ -17,6 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("LD_DP_CHECK_DUMP_AFTER", "240")), exit=True)     # a hang prints where every thread is
     import torch
     import torch.distributed as dist
     os.environ["LAYOUTDETR_SYNTHETIC_TOKENIZER"] = "1"
@@ -51,11 +53,19 @@ def main():
         for _ in range(steps):
             gs.run(hb, zs[0], zs[1])
         torch.cuda.synchronize()
-        ent = next(iter(gs.graphs.values()))
+        ent = dict(next(iter(gs.graphs.values())))
+        n_graphs = len(ent["graphs"])
+        ent = dict(exchange=ent.get("exchange"), graphs=[None] * n_graphs)
+        gs.close()                  # graphs with captured NCCL collectives must not outlive the process group
         return tr, ent
 
     out = {}
+
+    def log(msg):
+        print("[dp_check rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+    log("plain schedule ...")
     tr0, e0 = run(False, 0.0, 2)
+    log("overlapped schedule ...")
     g_plain = [tr0.flat[n].g.clone() for n in ("G", "D")]
     tr1, e1 = run(True, 0.0, 2)
     g_over = [tr1.flat[n].g.clone() for n in ("G", "D")]
@@ -67,6 +77,7 @@ def main():
     dist.all_gather(gg, g_over[0])
     out["grad_identical_across_ranks"] = bool(all(torch.equal(gg[0], x) for x in gg))
     del tr0, tr1, e0, e1
+    log("real steps ...")
     # a few real steps, dropout live: replicas must stay bit-identical
     tr2, e2 = run(True, 1e-4, 4, train_mode=True)
     sums = torch.stack([f.p.view(torch.int32).to(torch.int64).sum() for f in (tr2.flat["G"], tr2.flat["D"], tr2.flat_ema)])
