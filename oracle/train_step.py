@@ -67,3 +67,17 @@ def iteration(sdG, sdD, tok, inp):
     lf.backward()
     lr.backward()
     return float(lG), float(lf), float(lr)
+
+
+def phase_gradients(sdG, sdD, tok, inp, phase):
+    """{state_dict key: gradient} of one phase ('Gmain' | 'Dmain'), as reference loss.accumulate_gradients leaves them in `.grad`
+    (training/loss.py:88-218; Dmain = the fake-sample and the real-sample backward accumulated)."""
+    if phase == "Gmain":
+        leaves = _leafs(sdG)
+        gmain_loss(leaves, sdD, tok, inp).backward()
+    else:
+        leaves = _leafs(sdD)
+        lf, lr = dmain_loss(sdG, leaves, tok, inp)
+        lf.backward()
+        lr.backward()
+    return {k: v.grad for k, v in leaves.items() if v.requires_grad and v.grad is not None}

@@ -162,3 +162,33 @@ def test_pair_metric_arithmetic_matches_reference_goldens():
     lib.host_layout_pair_metrics(P(real), P(fake), P(v8), ctypes.c_long(B), N, P(iou), P(doc))
     torch.testing.assert_close(iou.double(), g["iou"], atol=1e-6, rtol=1e-5)
     torch.testing.assert_close(doc.double(), g["docsim"], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("phase", ["Gmain", "Dmain"])
+def test_oracle_train_step_gradients_match_reference(phase):
+    """oracle/train_step.py (the CPU baseline bench.py times, and the checker of the loss tests) against per-parameter gradients of
+    the reference's own accumulate_gradients (tests/golden/loss_b2_v8.pt, fp32 CPU, dropout off)."""
+    from helpers import build, state_dict_f32
+    from layoutdetr_b200.synthetic import SyntheticTokenizer, make_inputs
+    from oracle import train_step
+    g = golden("loss_b2_v8.pt")
+    sdG, sdD = state_dict_f32(build("G")), state_dict_f32(build("D"))
+    inp = make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"])
+    grads = train_step.phase_gradients(sdG, sdD, SyntheticTokenizer(), inp, phase)
+    ref = g["grads"][phase]
+    worst = (0.0, "")
+    n = 0
+    for k, n_ref in ref["norms"].items():
+        if n_ref < 1e-7:
+            continue
+        assert k in grads, "oracle produced no gradient for %s" % k
+        e = abs(float(grads[k].norm()) - n_ref) / n_ref
+        worst = max(worst, (e, k))
+        n += 1
+    for k, t in ref["small"].items():
+        if float(t.norm()) < 1e-7:
+            continue
+        e = float((grads[k] - t).norm() / t.norm())
+        worst = max(worst, (e, k + " (full tensor)"))
+    print(phase, "parameters compared:", n, "worst relative error: %.3e (%s)" % worst)
+    assert n > 250 and worst[0] < 2e-3, worst

@@ -1,5 +1,6 @@
 """GPU: gradient parity of one Gmain / Dmain phase (hand-written backward kernels) against gradients of the
-REAL reference (tests/golden/loss_b2_v8.pt: per-parameter norms + full small tensors, fp32 CPU, dropout off)."""
+REAL reference (tests/golden/loss_b2_v8.pt and, at the benched batch size, loss_b16_v8.pt: per-parameter norms + full small tensors,
+fp32 CPU, dropout off)."""
 import pytest
 import torch
 
@@ -29,10 +30,11 @@ def _phase_grads(phase, G, D, inp):
     return {k: p.grad for k, p in mod.named_parameters() if p.grad is not None}, loss.last[phase]
 
 
+@pytest.mark.parametrize("name", ["loss_b2_v8", "loss_b16_v8"])       # b16: the benched batch size (BASELINE configs[1])
 @pytest.mark.parametrize("phase", ["Gmain", "Dmain"])
-def test_phase_gradients_match_reference(phase):
+def test_phase_gradients_match_reference(phase, name):
     from layoutdetr_b200.synthetic import make_inputs
-    g = golden("loss_b2_v8.pt")
+    g = golden(name + ".pt")
     G = build("G").cuda()
     D = build("D").cuda()
     inp = _to_dev(make_inputs(g["batch"], n_valid=g["n_valid"], seed=g["inputs_seed"]))

@@ -1,4 +1,4 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571"
-./tools/microbench/fp32x2 > gpurun_out/r2_fp32x2_issue_rates.txt 2>&1; cat gpurun_out/r2_fp32x2_issue_rates.txt
-timeout 300 $TR tools/dp_check.py > gpurun_out/r2_dp_check.json 2> gpurun_out/r2_dp_check.err; echo "dp_check rc=$?"; tail -c 1500 gpurun_out/r2_dp_check.json; grep -v "Warning\|warn\|nested" gpurun_out/r2_dp_check.err | tail -30
-LD_DP_OVERLAP=1 timeout 300 $TR bench.py --gpus 2 --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_n2_overlap.json 2> gpurun_out/r2_bench_n2_overlap.err; echo "bench rc=$?"; tail -c 900 gpurun_out/r2_bench_n2_overlap.json; tail -5 gpurun_out/r2_bench_n2_overlap.err
+timeout 300 python tools/gemm_probe.py > gpurun_out/r2_gemm_epilogue_variants.txt 2>&1; cat gpurun_out/r2_gemm_epilogue_variants.txt
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_kernels_gpu.py -m gpu -q -x --timeout=600 2>&1 | tail -5
+timeout 1500 python -m pytest tests -m gpu -q --timeout=900 -s --deselect tests/test_gemm_gpu.py --deselect tests/test_kernels_gpu.py > gpurun_out/r2_pytest_gpu_c.log 2>&1; tail -15 gpurun_out/r2_pytest_gpu_c.log
+timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_c.json 2> gpurun_out/r2_bench_c.err; tail -c 1800 gpurun_out/r2_bench_c.json; tail -3 gpurun_out/r2_bench_c.err
