@@ -107,6 +107,29 @@ typedef struct ld_gemm_desc {
 
 int ld_gemm_bf16(const ld_gemm_desc* desc, void* stream);
 
+/* Implicit-GEMM convolution on the same kernel — replaces the cuDNN convolutions behind nn.Conv2d / F.conv2d of the ResNet-50
+ * body (training/detr_backbone.py:82-95, torchvision Bottleneck conv2 3x3 and the stride-2 1x1 downsample), of input_proj's
+ * neighbours and of the StyleGAN2 synthesis 3x3 layers (training/networks_stylegan2.py:30-83), forward, data gradient and weight
+ * gradient, WITHOUT a patch matrix in HBM: the TMA producer loads boxes of output pixels x 64 channels straight from the NHWC
+ * bf16 image at the tap's offset (out-of-image taps are zero-filled by the TMA unit; the convolution stride is the tensor map's
+ * traversal stride).  `img` is [B, H, W, C] bf16 contiguous, C % 64 == 0; Ho = (H + 2 pad - KH) / stride + 1 (same for W);
+ * a box of `mode == 1 ? 128 : 64` consecutive output pixels must be a rectangle of whole rows / whole images
+ * (Wo % box == 0, or box % Wo == 0 with Ho*Wo % box == 0 or box % (Ho*Wo) == 0) — LD_ERR_INVALID_ARG otherwise.
+ *   mode 1 (forward, and data gradient as a convolution of dy with the flipped, transposed weights):
+ *        D[M = B*Ho*Wo, N] = epilogue( patches(img)[M, K = KH*KW*C] @ desc->B[N, K]^T ),  K ordered (kh, kw, c);  desc->A is ignored
+ *   mode 2 (weight gradient):
+ *        D[M, N = KH*KW*C] = desc->A[K = B*Ho*Wo, M]^T (mn_major) @ patches(img)[K, N];  desc->B is ignored
+ * Everything else (epilogue terms, split_k, accumulate) is as in ld_gemm_bf16; nb1 = nb2 = 1. */
+typedef struct ld_conv_geom {
+    const void* img;
+    int32_t mode;
+    int32_t B, H, W, C;
+    int32_t Ho, Wo, KH, KW, stride, pad;
+    int32_t _pad;
+} ld_conv_geom;
+
+int ld_conv_gemm_bf16(const ld_gemm_desc* desc, const ld_conv_geom* geom, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * bias_act — replaces bias_act_plugin.bias_act (torch_utils/ops/bias_act.cpp:33-97, kernel bias_act.cu:24-148).
  * y = clamp(act(x + b[(i / stepB) % sizeB]) * gain); grad = 1 / 2 evaluate the first / second order

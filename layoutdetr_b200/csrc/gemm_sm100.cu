@@ -57,7 +57,20 @@ struct KParams {
     const float* cs; const float* cb; long col_sb1, col_sb2;
     const float* alpha_dev;
     int softmax, causal; float mask_value; const uint8_t* key_mask;
+    // implicit-GEMM convolution (ld_conv_gemm_bf16): 0 off, 1 = A rows are output pixels, 2 = B (MN-major) rows are output pixels
+    int cv_mode, cv_P, cv_Wo, cv_stride, cv_pad, cv_KW, cv_C;
 };
+
+// First output pixel of a box -> TMA coordinates (w, h, b) of tap (kh, kw) in the NHWC image.
+__device__ __forceinline__ void conv_coords(const KParams& p, int pix0, int kh, int kw, int& cw, int& chh, int& cb) {
+    const int b0 = pix0 / p.cv_P;
+    const int rem = pix0 - b0 * p.cv_P;
+    const int y0 = rem / p.cv_Wo;
+    const int x0 = rem - y0 * p.cv_Wo;
+    cw = x0 * p.cv_stride + kw - p.cv_pad;
+    chh = y0 * p.cv_stride + kh - p.cv_pad;
+    cb = b0;
+}
 
 struct Tile {
     int b1, b2, m0, n0, kb_begin, kb_end;
@@ -461,7 +474,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                     uint8_t* sa = smem + stage * SBYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     const int k0 = kb * BK;
-                    if (!p.a_mn) {
+                    if (p.cv_mode == 1) {
+                        // K block -> (tap, channel block); the A tile is a box of 128 output pixels x 64 channels of the image
+                        const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
+                        const int kh = tap / p.cv_KW, kw = tap - kh * p.cv_KW;
+                        int cw, chh, cb;
+                        conv_coords(p, am0, kh, kw, cw, chh, cb);
+                        if (TWO_SM) tma_load_4d_2sm(sa, &tmA, &full_bar[stage], c0, cw, chh, cb);
+                        else tma_load_4d(sa, &tmA, &full_bar[stage], c0, cw, chh, cb);
+                    } else if (!p.a_mn) {
                         if (TWO_SM) tma_load_4d_2sm(sa, &tmA, &full_bar[stage], k0, am0, tl.b2, tl.b1);
                         else tma_load_4d(sa, &tmA, &full_bar[stage], k0, am0, tl.b2, tl.b1);
                     } else {
@@ -471,7 +492,19 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                             else tma_load_4d(sa + j * 8192, &tmA, &full_bar[stage], am0 + 64 * j, k0, tl.b2, tl.b1);
                         }
                     }
-                    if (!p.b_mn) {
+                    if (p.cv_mode == 2) {
+                        // MN-major B: 64 K-rows = 64 output pixels, each 64-wide N block = 64 channels of one tap
+                        for (int j = 0; j < b_rows / 64; ++j) {
+                            const int n = bn0 + 64 * j;
+                            const int tap = n / p.cv_C, c0 = n - tap * p.cv_C;
+                            const int kh = tap / p.cv_KW, kw = tap - kh * p.cv_KW;
+                            int cw, chh, cb;
+                            conv_coords(p, k0, kh, kw, cw, chh, cb);
+                            const int cc = n < p.N ? c0 : p.cv_C;                 // N overhang: out-of-range channel -> zero fill
+                            if (TWO_SM) tma_load_4d_2sm(sb + j * 8192, &tmB, &full_bar[stage], cc, cw, chh, cb);
+                            else tma_load_4d(sb + j * 8192, &tmB, &full_bar[stage], cc, cw, chh, cb);
+                        }
+                    } else if (!p.b_mn) {
                         if (TWO_SM) tma_load_4d_2sm(sb, &tmB, &full_bar[stage], k0, bn0, tl.b2, tl.b1);
                         else tma_load_4d(sb, &tmB, &full_bar[stage], k0, bn0, tl.b2, tl.b1);
                     } else {
@@ -639,7 +672,59 @@ int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K
 
 }  // namespace
 
-extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
+namespace {
+
+// Tensor map of the image operand of an implicit-GEMM convolution: dims (C, W, H, B), box = `pix` output pixels x 64 channels.
+int make_conv_map(CUtensorMap* tm, const ld_conv_geom& g, int pix) {
+    using namespace ld;
+    if (!g.img || (reinterpret_cast<uintptr_t>(g.img) & 15) != 0) { set_last_error("conv gemm: image pointer null or not 16-byte aligned"); return LD_ERR_ALIGNMENT; }
+    if (g.C % 64 != 0 || g.C <= 0) { set_last_error("conv gemm: C = %d must be a positive multiple of 64", g.C); return LD_ERR_INVALID_ARG; }
+    if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.KH <= 0 || g.KW <= 0 || g.stride <= 0 || g.pad < 0) { set_last_error("conv gemm: bad geometry"); return LD_ERR_INVALID_ARG; }
+    if (g.Ho != (g.H + 2 * g.pad - g.KH) / g.stride + 1 || g.Wo != (g.W + 2 * g.pad - g.KW) / g.stride + 1 || g.Ho <= 0 || g.Wo <= 0) {
+        set_last_error("conv gemm: Ho x Wo = %d x %d inconsistent with H x W = %d x %d, k = %d x %d, stride %d, pad %d", g.Ho, g.Wo, g.H, g.W, g.KH, g.KW, g.stride, g.pad);
+        return LD_ERR_INVALID_ARG;
+    }
+    const int P = g.Ho * g.Wo;
+    int bw, bh, bb;
+    if (g.Wo >= pix) { if (g.Wo % pix) goto bad; bw = pix; bh = 1; bb = 1; }
+    else {
+        if (pix % g.Wo) goto bad;
+        bw = g.Wo;
+        if (P >= pix) { if (P % pix) goto bad; bh = pix / g.Wo; bb = 1; }
+        else { if (pix % P) goto bad; bh = g.Ho; bb = pix / P; }
+    }
+    if (bw * g.stride > 256 || bh * g.stride > 256) goto bad;
+    {
+        const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+        const uint64_t strides[3] = {(uint64_t)g.C * 2, (uint64_t)g.W * g.C * 2, (uint64_t)g.H * g.W * g.C * 2};
+        const uint32_t box[4] = {64u, (uint32_t)(bw * g.stride), (uint32_t)(bh * g.stride), (uint32_t)bb};
+        const uint32_t estr[4] = {1u, (uint32_t)g.stride, (uint32_t)g.stride, 1u};
+        return encode_tmap_bf16_4d_box(tm, g.img, dims, strides, box, estr);
+    }
+bad:
+    set_last_error("conv gemm: a box of %d output pixels is not a rectangle of whole rows / images for Ho x Wo = %d x %d (stride %d)", pix, g.Ho, g.Wo, g.stride);
+    return LD_ERR_INVALID_ARG;
+}
+
+int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream);
+
+}  // namespace
+
+extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) { return gemm_launch(d, nullptr, stream); }
+
+extern "C" int ld_conv_gemm_bf16(const ld_gemm_desc* d, const ld_conv_geom* g, void* stream) {
+    using namespace ld;
+    LD_CHECK_ARG(d != nullptr && g != nullptr, "conv gemm: null descriptor");
+    LD_CHECK_ARG(g->mode == 1 || g->mode == 2, "conv gemm: mode must be 1 (forward / data gradient) or 2 (weight gradient)");
+    LD_CHECK_ARG(d->nb1 == 1 && d->nb2 == 1 && !d->softmax, "conv gemm: no batch dims, no softmax epilogue");
+    const long pixels = (long)g->B * g->Ho * g->Wo, taps = (long)g->KH * g->KW * g->C;
+    if (g->mode == 1) LD_CHECK_ARG(d->M == pixels && d->K == taps && !d->B.mn_major, "conv gemm (mode 1): M = %d, K = %d must be B*Ho*Wo = %ld, KH*KW*C = %ld", d->M, d->K, pixels, taps);
+    if (g->mode == 2) LD_CHECK_ARG(d->K == pixels && d->N == taps && d->A.mn_major, "conv gemm (mode 2): K = %d, N = %d must be B*Ho*Wo = %ld, KH*KW*C = %ld (A mn_major)", d->K, d->N, pixels, taps);
+    return gemm_launch(d, g, stream);
+}
+
+namespace {
+int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     using namespace ld;
     LD_CHECK_ARG(d != nullptr, "gemm: null descriptor");
     LD_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0 && d->nb1 > 0 && d->nb2 > 0, "gemm: non-positive dims M=%d N=%d K=%d nb=%dx%d", d->M, d->N, d->K, d->nb1, d->nb2);
@@ -667,6 +752,11 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     p.cs = d->col_scale; p.cb = d->col_bias; p.col_sb1 = d->col_sb1; p.col_sb2 = d->col_sb2;
     p.alpha_dev = d->alpha_dev;
     p.softmax = d->softmax ? 1 : 0; p.causal = d->causal ? 1 : 0; p.mask_value = d->mask_value; p.key_mask = d->key_mask;
+    if (cg) {
+        p.cv_mode = cg->mode; p.cv_P = cg->Ho * cg->Wo; p.cv_Wo = cg->Wo; p.cv_stride = cg->stride; p.cv_pad = cg->pad;
+        p.cv_KW = cg->KW; p.cv_C = cg->C;
+        if (cg->mode == 1) p.a_mn = 0; else p.b_mn = 1;
+    }
 
     const int sms = sm_count();
     const int cta_limit = cta_limit_for(stream);       // persistent grid cap of this stream's lane (default: every SM)
@@ -723,9 +813,9 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     if (p.act == LD_ACT_GELU && p.post_gain != 1.0f) p.fast = 0;
 
     alignas(64) CUtensorMap tmA, tmB;
-    int e = make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
+    int e = (cg && cg->mode == 1) ? make_conv_map(&tmA, *cg, BM) : make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
     if (e) return e;
-    e = make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, two_sm ? bn / 2 : bn);
+    e = (cg && cg->mode == 2) ? make_conv_map(&tmB, *cg, BK) : make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, two_sm ? bn / 2 : bn);
     if (e) return e;
 
     static bool attr_set = false;
@@ -748,3 +838,4 @@ extern "C" int ld_gemm_bf16(const ld_gemm_desc* d, void* stream) {
     LD_LAUNCH_CHECK("gemm launch");
     return 0;
 }
+}  // namespace

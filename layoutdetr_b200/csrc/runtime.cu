@@ -97,6 +97,30 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4
     return 0;
 }
 
+// General form: explicit box and traversal strides per dimension (implicit-GEMM convolution: a box of output pixels over an
+// NHWC image, elementStrides = the convolution stride on W / H).
+int encode_tmap_bf16_4d_box(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                            const uint32_t box[4], const uint32_t estr[4]) {
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point unavailable (driver too old / no GPU)"); return LD_ERR_DRIVER; }
+    cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+    cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t e[4] = {estr[0], estr[1], estr[2], estr[3]};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u] estr=[%u,%u,%u,%u]",
+                       (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                       (unsigned long long)dims[3], box[0], box[1], box[2], box[3], estr[0], estr[1], estr[2], estr[3]);
+        return LD_ERR_DRIVER;
+    }
+    return 0;
+}
+
 }  // namespace ld
 
 extern "C" {

@@ -9,4 +9,6 @@ void count_launch(int n = 1);
 // strides_bytes = byte strides of dims 1..3 (multiples of 16).
 int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                         uint32_t box_inner, uint32_t box_outer);
+int encode_tmap_bf16_4d_box(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                            const uint32_t box[4], const uint32_t estr[4]);
 }  // namespace ld

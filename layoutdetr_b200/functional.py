@@ -9,6 +9,7 @@ Conventions
     training loop only ever reads `.grad` (reference training/training_loop.py:303-312).
 """
 import math
+import os
 
 import torch
 
@@ -577,8 +578,31 @@ def conv_weight_bf16(weight):
     return E.derived((weight,), "ohwi", _make_ohwi)
 
 
+def _make_flipT(weight):
+    """OIHW -> bf16 [Cin, KH*KW*Cout] with the taps reversed: the weights of the convolution that maps dy to dx (stride 1)."""
+    Cin = weight.shape[1]
+    w = weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, -1).contiguous()
+    return K.cast_pad(w, torch.bfloat16, E.pad8(w.shape[1]))
+
+
+def conv_weight_flipT_bf16(weight):
+    return E.derived((weight,), "ihwo_flip", _make_flipT)
+
+
+IMPLICIT_CONV = os.environ.get("LD_CONV_IMPLICIT", "1") != "0"     # 0: every convolution goes through an explicit patch matrix
+
+
+def _conv_geom(img, mode, B, H, W, C, Ho, Wo, KH, KW, stride, pad):
+    return dict(img=img, mode=mode, B=B, H=H, W=W, C=C, Ho=Ho, Wo=Wo, KH=KH, KW=KW, stride=stride, pad=pad)
+
+
 class Conv2dFn(_Fn):
     """y = act(conv(x, W) * scale + shift + residual) on channels-last bf16 activations.
+
+    Implicit GEMM (ld_conv_gemm_bf16: the TMA producer reads boxes of pixels x 64 channels straight from the NHWC image, no
+    patch matrix in HBM) whenever the channel count is a multiple of 64 and a box of output pixels is a rectangle of whole rows —
+    forward, the stride-1 data gradient (a convolution of dy with the flipped, transposed weights) and the weight gradient;
+    the 3-channel stem and odd geometries keep the explicit im2col / col2im path.
 
     x: [B*H*W, Cin] bf16 (NHWC rows).  scale/shift: fp32 [Cout] (folded FrozenBatchNorm2d, reference
     training/detr_backbone.py:55-65, or a conv bias).  Reference convs: torchvision resnet50 via
@@ -590,15 +614,18 @@ class Conv2dFn(_Fn):
         Cout, Cin, KH, KW = weight.shape
         w16 = conv_weight_bf16(weight)
         direct = (KH == 1 and KW == 1 and stride == 1 and pad == 0 and Cin % 8 == 0)
-        if direct:
-            cols, Ho, Wo = x, H, W
-        else:
-            cols, Ho, Wo = K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)
+        Ho, Wo = K.conv_out_size(H, KH, stride, pad), K.conv_out_size(W, KW, stride, pad)
         M = B * Ho * Wo
         out = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
-        K.gemm(M, Cout, cols.shape[1], K.Op(cols, cols.stride(0)), K.Op(w16, w16.stride(0)), K.Out(out, Cout),
-               act=act, R=K.Out(residual, residual.stride(0)) if residual is not None else None,
-               col_scale=scale, col_bias=shift.detach() if shift is not None else None)
+        epi = dict(act=act, R=K.Out(residual, residual.stride(0)) if residual is not None else None,
+                   col_scale=scale, col_bias=shift.detach() if shift is not None else None)
+        implicit = (not direct and IMPLICIT_CONV and Cin % 64 == 0 and x.is_contiguous() and K.conv_box_ok(Ho, Wo, stride, 128))
+        if implicit:
+            K.gemm(M, Cout, KH * KW * Cin, K.Op(x, Cin), K.Op(w16, w16.stride(0)), K.Out(out, Cout),
+                   conv=_conv_geom(x, 1, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad), **epi)
+        else:
+            cols = x if direct else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0]
+            K.gemm(M, Cout, cols.shape[1], K.Op(cols, cols.stride(0)), K.Op(w16, w16.stride(0)), K.Out(out, Cout), **epi)
         ctx.geom = (B, H, W, stride, pad, Ho, Wo, direct)
         ctx.weight, ctx.act, ctx.scale = weight, act, scale
         ctx.shift_param = shift if isinstance(shift, torch.nn.Parameter) else None
@@ -630,24 +657,35 @@ class Conv2dFn(_Fn):
             _bgrad(ctx.shift_param, 0, Cout, dpre if dpre is not None else dy)
         w16 = conv_weight_bf16(weight)
         dx = None
+        dconv = dconv.contiguous()
         if ctx.needs_input_grad[0]:
-            dcols = _dgrad(dconv, w16, w16.shape[1])
-            dx = dcols if direct else K.col2im(dcols, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad)
+            same = stride == 1 and Ho == H and Wo == W and KH == KW
+            if (not direct and IMPLICIT_CONV and same and Cout % 64 == 0 and K.conv_box_ok(H, W, 1, 128)):
+                # dx = conv(dy, flipped weights), pad' = k - 1 - pad: no [M, 9 Cin] temporary, no col2im pass
+                wf = conv_weight_flipT_bf16(weight)
+                dx = torch.empty((B * H * W, Cin), dtype=torch.bfloat16, device=x.device)
+                K.gemm(B * H * W, Cin, KH * KW * Cout, K.Op(dconv, Cout), K.Op(wf, wf.stride(0)), K.Out(dx, Cin),
+                       conv=_conv_geom(dconv, 1, B, Ho, Wo, Cout, H, W, KH, KW, 1, KH - 1 - pad))
+            else:
+                dcols = _dgrad(dconv, w16, w16.shape[1])
+                dx = dcols if direct else K.col2im(dcols, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad)
         if _needs(weight):
-            cols = x if direct else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0]
             g = E.grad_buffer(weight)
             M = dconv.shape[0]
             Kreal = KH * KW * Cin
             sk = E.wgrad_split_k(Cout, Kreal, M)
+            implicit = (not direct and IMPLICIT_CONV and Cin % 64 == 0 and x.is_contiguous() and K.conv_box_ok(Ho, Wo, stride, 64))
+            cv = _conv_geom(x, 2, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad) if implicit else None
+            cols = x if (direct or implicit) else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0]
             if KH == 1 and KW == 1:
                 g2 = g.view(Cout, Cin)
                 K.gemm(Cout, Cin, M, K.Op(dconv, Cout, mn=True), K.Op(cols, cols.stride(0), mn=True), K.Out(g2, Cin),
-                       accumulate=2 if sk > 1 else 1, split_k=sk)
+                       accumulate=2 if sk > 1 else 1, split_k=sk, conv=cv)
             else:
                 tmp = torch.zeros((Cout, Kreal), dtype=torch.float32, device=x.device) if sk > 1 else \
                     torch.empty((Cout, Kreal), dtype=torch.float32, device=x.device)
                 K.gemm(Cout, Kreal, M, K.Op(dconv, Cout, mn=True), K.Op(cols, cols.stride(0), mn=True), K.Out(tmp, Kreal),
-                       accumulate=2 if sk > 1 else 0, split_k=sk)
+                       accumulate=2 if sk > 1 else 0, split_k=sk, conv=cv)
                 g.add_(tmp.view(Cout, KH, KW, Cin).permute(0, 3, 1, 2))
         return dx, None, None, None, dres, None, None
 

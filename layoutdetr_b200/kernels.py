@@ -55,6 +55,28 @@ class _GemmDesc(ctypes.Structure):
                 ("softmax", c_int32), ("causal", c_int32), ("mask_value", c_float), ("_pad2", c_int32), ("key_mask", c_void_p)]
 
 
+class _ConvGeom(ctypes.Structure):
+    _fields_ = [("img", c_void_p), ("mode", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
+                ("Ho", c_int32), ("Wo", c_int32), ("KH", c_int32), ("KW", c_int32), ("stride", c_int32), ("pad", c_int32),
+                ("_pad", c_int32)]
+
+
+def conv_box_ok(Ho, Wo, stride, pix):
+    """Can `pix` consecutive output pixels be loaded as ONE TMA box (whole rows / whole images)?  Mirrors make_conv_map."""
+    P = Ho * Wo
+    if Wo >= pix:
+        ok, bw, bh = Wo % pix == 0, pix, 1
+    else:
+        if pix % Wo:
+            return False
+        bw = Wo
+        if P >= pix:
+            ok, bh = P % pix == 0, pix // Wo
+        else:
+            ok, bh = pix % P == 0, Ho
+    return bool(ok and bw * stride <= 256 and bh * stride <= 256)
+
+
 class Op:
     """A GEMM operand view: base tensor (bf16) + element offset, leading dim, batch strides, major-ness."""
     __slots__ = ("t", "off", "ld", "sb1", "sb2", "mn")
@@ -84,8 +106,10 @@ GEMM_LOG = None        # tools/lane_trace.py sets this to a list: one (M, N, K, 
 
 
 def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0, accumulate=0, split_k=1,
-         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None, softmax=None):
-    """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics."""
+         R=None, col_scale=None, col_bias=None, col_sb1=0, col_sb2=0, aux=None, block_n=0, alpha_dev=None, softmax=None, conv=None):
+    """D = epilogue(A @ B^T) on tcgen05 tensor cores; see ld_gemm_bf16 in the header for semantics.
+    conv = dict(img, mode, B, H, W, C, Ho, Wo, KH, KW, stride, pad): implicit-GEMM convolution (ld_conv_gemm_bf16) — the operand the
+    mode replaces (A for mode 1, B for mode 2) is ignored and may be any bf16 tensor."""
     _cuda(A.t, B.t, D.t)
     if GEMM_LOG is not None:
         import sys
@@ -135,6 +159,17 @@ def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0,
         if km is not None:
             assert km.dtype == torch.uint8 and km.is_contiguous()
             d.key_mask = km.data_ptr()
+    if conv is not None:
+        img = conv["img"]
+        _cuda(img)
+        if img.dtype != torch.bfloat16 or not img.is_contiguous():
+            raise TypeError("conv gemm: the image must be a contiguous bf16 NHWC tensor")
+        g = _ConvGeom()
+        g.img, g.mode = img.data_ptr(), conv["mode"]
+        g.B, g.H, g.W, g.C = conv["B"], conv["H"], conv["W"], conv["C"]
+        g.Ho, g.Wo, g.KH, g.KW, g.stride, g.pad = conv["Ho"], conv["Wo"], conv["KH"], conv["KW"], conv["stride"], conv["pad"]
+        check(lib().ld_conv_gemm_bf16(ctypes.byref(d), ctypes.byref(g), _stream()), "ld_conv_gemm_bf16")
+        return
     check(lib().ld_gemm_bf16(ctypes.byref(d), _stream()), "ld_gemm_bf16")
 
 
