@@ -335,6 +335,24 @@ template <int ACT, bool OUT_BF16, int RES>
 __device__ __forceinline__ void epilogue_fast_tile(const KParams& p, const Tile& tl, uint32_t taddr, int col_begin, int col_end,
                                                    bool row_ok, float alpha, uint32_t cs_a, uint32_t cb_a,
                                                    long d_off, long r_off, long c_off, long d_base, int row0, uint32_t stg_a) {
+    if (tl.n0 + col_end <= p.N && col_end - col_begin == 128) {
+        // Common case (this warp's four 32-column chunks are all inside the matrix): the TMEM load of chunk i + 1 is in flight
+        // while chunk i is converted and stored, so the warp waits for one TMEM round trip per tile instead of four.
+        uint32_t ra[32], rb[32];
+        tmem_ld_x32(taddr + col_begin, ra);
+        tmem_ld_wait();
+        tmem_ld_x32(taddr + col_begin + 32, rb);
+        epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, ra, alpha, cs_a, cb_a, col_begin, tl.n0 + col_begin, d_base, row0, row_ok ? r_off : -1, stg_a);
+        tmem_ld_wait();
+        tmem_ld_x32(taddr + col_begin + 64, ra);
+        epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, rb, alpha, cs_a, cb_a, col_begin + 32, tl.n0 + col_begin + 32, d_base, row0, row_ok ? r_off : -1, stg_a);
+        tmem_ld_wait();
+        tmem_ld_x32(taddr + col_begin + 96, rb);
+        epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, ra, alpha, cs_a, cb_a, col_begin + 64, tl.n0 + col_begin + 64, d_base, row0, row_ok ? r_off : -1, stg_a);
+        tmem_ld_wait();
+        epilogue_fast_chunk<ACT, OUT_BF16, RES>(p, rb, alpha, cs_a, cb_a, col_begin + 96, tl.n0 + col_begin + 96, d_base, row0, row_ok ? r_off : -1, stg_a);
+        return;
+    }
     for (int c0 = col_begin; c0 < col_end; c0 += 32) {
         const int n_base = tl.n0 + c0;
         if (n_base >= p.N) break;                       // warp-uniform
