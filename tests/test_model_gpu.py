@@ -75,7 +75,8 @@ def test_discriminator_forward_matches_reference_golden(D_cuda, name):
     scale = max(1.0, float(ref["logit_disc"].abs().max()))
     assert rep["logit_disc"] < 5e-2 * scale and rep["logit_disc_uncond"] < 5e-2 * max(1.0, float(ref["logit_disc_uncond"].abs().max())), rep
     assert rep["loss_lm"] < 2e-2 * float(ref["loss_lm"]), rep
-    assert rep["bg_rec"] < 0.25, rep        # max over pixels, in units of the image std; 13 bf16 conv layers
+    # background reconstruction through 13 bf16 conv layers, in units of the image std: rms over pixels and the single worst pixel
+    assert rep["bg_rec_rms"] < 0.06 and rep["bg_rec"] < 0.3, rep
 
 
 def test_generator_matches_cpu_oracle_other_seed(G_cuda):

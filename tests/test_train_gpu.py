@@ -65,5 +65,6 @@ def test_phase_gradients_match_reference(phase, name):
     frac_ok = sum(1 for r in rows if r[0] < 0.10) / max(1, len(rows))
     med = sorted(r[0] for r in rows)[len(rows) // 2]
     print("params compared %d, median rel norm err %.4f, within 10%%: %.3f" % (len(rows), med, frac_ok))
-    assert med < 0.03 and frac_ok > 0.97
-    assert sum(1 for c, _ in cos_rows if c > 0.98) / max(1, len(cos_rows)) > 0.95
+    # measured on B200 (bf16 tensor cores vs the fp32 reference): median 0.2-1 %, worst parameter 4.5 %, worst cosine 0.997
+    assert med < 0.02 and frac_ok == 1.0 and rows[0][0] < 0.08, (med, frac_ok, rows[0])
+    assert cos_rows[0][0] > 0.99, cos_rows[0]
