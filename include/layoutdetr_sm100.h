@@ -230,6 +230,13 @@ int ld_demod_bias_act_fwd(const void* x, int x_dtype, const float* d, const floa
 int ld_demod_bias_act_bwd(const void* dy_bf16, const void* y_bf16, const void* x, int x_dtype, const float* d,
                           void* dx_bf16, float* dd, float* dbias, int B, int64_t pixels, int C, int act, float gain, void* stream);
 int ld_channel_dot(const void* a, int a_dtype, const void* g_bf16, float* out, int B, int64_t pixels, int C, void* stream);
+/* Deterministic forms of the two style-gradient reductions (bf16 rows, C % 8 == 0): fixed-order sums through a caller workspace of
+ * ld_style_reduce_ws_floats(B, pixels, C) floats (twice that for ld_demod_bias_act_bwd_ws), no floating-point atomics — results are
+ * bit-identical from run to run.  dd / dbias / out are accumulated into (+=), as in the atomics forms. */
+int64_t ld_style_reduce_ws_floats(int B, int64_t pixels, int C);
+int ld_demod_bias_act_bwd_ws(const void* dy_bf16, const void* y_bf16, const void* x_bf16, const float* d, void* dx_bf16, float* dd, float* dbias,
+                             float* ws, int64_t ws_floats, int B, int64_t pixels, int C, int act, float gain, void* stream);
+int ld_channel_dot_ws(const void* a_bf16, const void* g_bf16, float* out, float* ws, int64_t ws_floats, int B, int64_t pixels, int C, void* stream);
 
 /* Small elementwise helpers used between GEMMs. */
 int ld_cast_pad(const void* src, int src_dtype, int64_t lds, void* dst, int dst_dtype, int64_t ldd,

@@ -697,6 +697,104 @@ demod_bias_act_bwd_vec_kernel(const uint4* __restrict__ dy, const uint4* __restr
     }
 }
 
+// Deterministic variants of the two style-gradient reductions (ld_*_ws): every thread row keeps its partial sums in its own
+// shared-memory slot, the block adds them in a fixed order and writes ONE partial per (block, sample, channel) to a caller
+// workspace; partial_sum_accum_kernel then adds the blocks in index order.  No floating-point atomics anywhere, so the result
+// does not depend on scheduling (the atomics versions flip single bf16 roundings downstream from run to run).
+__global__ void __launch_bounds__(256)
+demod_bias_act_bwd_det_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, const uint4* __restrict__ x,
+                              const float* __restrict__ d, uint4* __restrict__ dx, float* __restrict__ ws_dd, float* __restrict__ ws_db,
+                              long pixels, int C, int act, float gain, int pix_per_block) {
+    extern __shared__ float red[];                       // [prows][2][C]
+    const int C8 = C >> 3;
+    const int b = blockIdx.y;
+    const int cg = threadIdx.x % C8, prow = threadIdx.x / C8, prows = blockDim.x / C8;
+    float dc[8], sd[8], sb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dc[k] = d ? d[(long)b * C + cg * 8 + k] : 1.f; sd[k] = 0.f; sb[k] = 0.f; }
+    const long p0 = (long)blockIdx.x * pix_per_block;
+    const long p1 = min(pixels, p0 + pix_per_block);
+    if (prow < prows) {
+        for (long p = p0 + prow; p < p1; p += prows) {
+            const long i = ((long)b * pixels + p) * C8 + cg;
+            const uint4 g4 = dy[i], y4 = y[i], x4 = x[i];
+            const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, yw[4] = {y4.x, y4.y, y4.z, y4.w}, xw[4] = {x4.x, x4.y, x4.z, x4.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float g0, g1, y0, y1, x0, x1;
+                unpack_bf16x2(gw[k], g0, g1); unpack_bf16x2(yw[k], y0, y1); unpack_bf16x2(xw[k], x0, x1);
+                g0 *= gain; g1 *= gain;
+                if (act == LD_ACT_LRELU) { if (y0 < 0.f) g0 *= 0.2f; if (y1 < 0.f) g1 *= 0.2f; }
+                sd[2 * k] += g0 * x0; sd[2 * k + 1] += g1 * x1;
+                sb[2 * k] += g0; sb[2 * k + 1] += g1;
+                o[k] = pack_bf16x2(g0 * dc[2 * k], g1 * dc[2 * k + 1]);
+            }
+            dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { red[(prow * 2 + 0) * C + cg * 8 + k] = sd[k]; red[(prow * 2 + 1) * C + cg * 8 + k] = sb[k]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, bsum = 0.f;
+        for (int r = 0; r < prows; ++r) { a += red[(r * 2 + 0) * C + c]; bsum += red[(r * 2 + 1) * C + c]; }
+        const long o = ((long)blockIdx.x * gridDim.y + b) * C + c;
+        ws_dd[o] = a;
+        ws_db[o] = bsum;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+channel_dot_det_kernel(const uint4* __restrict__ a, const uint4* __restrict__ g, float* __restrict__ ws, long pixels, int C, int pix_per_block) {
+    extern __shared__ float red[];                       // [prows][C]
+    const int C8 = C >> 3;
+    const int b = blockIdx.y;
+    const int cg = threadIdx.x % C8, prow = threadIdx.x / C8, prows = blockDim.x / C8;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long p0 = (long)blockIdx.x * pix_per_block;
+    const long p1 = min(pixels, p0 + pix_per_block);
+    if (prow < prows) {
+        for (long p = p0 + prow; p < p1; p += prows) {
+            const long i = ((long)b * pixels + p) * C8 + cg;
+            const uint4 a4 = a[i], g4 = g[i];
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a0, a1, g0, g1;
+                unpack_bf16x2(aw[k], a0, a1); unpack_bf16x2(gw[k], g0, g1);
+                s[2 * k] += a0 * g0; s[2 * k + 1] += a1 * g1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[prow * C + cg * 8 + k] = s[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < prows; ++r) t += red[r * C + c];
+        ws[((long)blockIdx.x * gridDim.y + b) * C + c] = t;
+    }
+}
+
+// out[i] += sum over (block k, segment f) of ws[k * n + f * per + i], per = n / fold (fold > 1: the bias gradient also sums over the
+// batch).  One warp per output element: lane l adds the terms l, l + 32, ... in order, then a fixed shuffle tree — the same
+// association every run, so the result is deterministic.
+__global__ void __launch_bounds__(256) partial_sum_accum_kernel(const float* __restrict__ ws, float* __restrict__ out, int nblk, long n, int fold) {
+    const long per = n / fold;
+    const long i = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= per) return;
+    const int lane = threadIdx.x & 31;
+    const int terms = nblk * fold;
+    float t = 0.f;
+    for (int q = lane; q < terms; q += 32) {
+        const int k = q / fold, f = q - k * fold;
+        t += ws[(long)k * n + (long)f * per + i];
+    }
+    t = warp_sum(t);
+    if (lane == 0) out[i] += t;
+}
+
 __global__ void __launch_bounds__(256)
 channel_dot_vec_kernel(const uint4* __restrict__ a, const uint4* __restrict__ g, float* __restrict__ out, long pixels, int C, int pix_per_block) {
     extern __shared__ float red[];                       // [C]
@@ -770,6 +868,59 @@ int ld_demod_bias_act_bwd(const void* dy_bf16, const void* y_bf16, const void* x
     else demod_bias_act_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy_bf16, (const __nv_bfloat16*)y_bf16, (const __nv_bfloat16*)x, d, (__nv_bfloat16*)dx_bf16, dd, dbias, pixels, C, act, gain, ppb);
     ld::count_launch();
     LD_LAUNCH_CHECK("demod_bias_act_bwd");
+    return 0;
+}
+
+// number of pixel blocks the vectorised style reductions use for (B, pixels, C): the _ws variants need nblk * B * C floats per sum
+static inline void style_reduce_geom(int B, int64_t pixels, int C, int& prows, int& ppbv, unsigned& nblk) {
+    prows = 256 / (C / 8);
+    const long want_blocks = std::max<long>(1, (long)ld::sm_count() * 4 / B);
+    ppbv = (int)std::max<long>(prows, (pixels + want_blocks - 1) / want_blocks);
+    nblk = (unsigned)((pixels + ppbv - 1) / ppbv);
+}
+static inline bool style_vec_ok(int C) { return C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && C <= 2048; }
+
+int64_t ld_style_reduce_ws_floats(int B, int64_t pixels, int C) {
+    if (B <= 0 || pixels <= 0 || C <= 0 || !style_vec_ok(C)) return 0;
+    int prows, ppbv; unsigned nblk;
+    style_reduce_geom(B, pixels, C, prows, ppbv, nblk);
+    return (int64_t)nblk * B * C;
+}
+
+int ld_demod_bias_act_bwd_ws(const void* dy_bf16, const void* y_bf16, const void* x_bf16, const float* d, void* dx_bf16, float* dd, float* dbias,
+                             float* ws, int64_t ws_floats, int B, int64_t pixels, int C, int act, float gain, void* stream) {
+    LD_CHECK_ARG(dy_bf16 && y_bf16 && x_bf16 && dx_bf16 && ws && B > 0 && pixels > 0 && C > 0, "demod_bias_act_bwd_ws: bad argument");
+    LD_CHECK_ARG(style_vec_ok(C) && ((((uintptr_t)dy_bf16 | (uintptr_t)y_bf16 | (uintptr_t)x_bf16 | (uintptr_t)dx_bf16) & 15) == 0),
+                 "demod_bias_act_bwd_ws: needs bf16 rows of C %% 8 == 0 channels, 16-byte aligned");
+    int prows, ppbv; unsigned nblk;
+    style_reduce_geom(B, pixels, C, prows, ppbv, nblk);
+    const long per = (long)nblk * B * C;
+    LD_CHECK_ARG(ws_floats >= 2 * per, "demod_bias_act_bwd_ws: workspace of %lld floats, need %ld", (long long)ws_floats, 2 * per);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 gridv(nblk, (unsigned)B);
+    demod_bias_act_bwd_det_kernel<<<gridv, 256, (size_t)prows * 2 * C * sizeof(float), st>>>(
+        (const uint4*)dy_bf16, (const uint4*)y_bf16, (const uint4*)x_bf16, d, (uint4*)dx_bf16, ws, ws + per, pixels, C, act, gain, ppbv);
+    const long n = (long)B * C;
+    if (dd) partial_sum_accum_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws, dd, (int)nblk, n, 1);
+    if (dbias) partial_sum_accum_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(ws + per, dbias, (int)nblk, n, B);
+    ld::count_launch(1 + (dd ? 1 : 0) + (dbias ? 1 : 0));
+    LD_LAUNCH_CHECK("demod_bias_act_bwd_ws");
+    return 0;
+}
+
+int ld_channel_dot_ws(const void* a_bf16, const void* g_bf16, float* out, float* ws, int64_t ws_floats, int B, int64_t pixels, int C, void* stream) {
+    LD_CHECK_ARG(a_bf16 && g_bf16 && out && ws && B > 0 && pixels > 0 && C > 0, "channel_dot_ws: bad argument");
+    LD_CHECK_ARG(style_vec_ok(C) && ((((uintptr_t)a_bf16 | (uintptr_t)g_bf16) & 15) == 0), "channel_dot_ws: needs bf16 rows of C %% 8 == 0 channels, 16-byte aligned");
+    int prows, ppbv; unsigned nblk;
+    style_reduce_geom(B, pixels, C, prows, ppbv, nblk);
+    const long n = (long)B * C;
+    LD_CHECK_ARG(ws_floats >= (long)nblk * n, "channel_dot_ws: workspace of %lld floats, need %ld", (long long)ws_floats, (long)nblk * n);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 gridv(nblk, (unsigned)B);
+    channel_dot_det_kernel<<<gridv, 256, (size_t)prows * C * sizeof(float), st>>>((const uint4*)a_bf16, (const uint4*)g_bf16, ws, pixels, C, ppbv);
+    partial_sum_accum_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ws, out, (int)nblk, n, 1);
+    ld::count_launch(2);
+    LD_LAUNCH_CHECK("channel_dot_ws");
     return 0;
 }
 

@@ -4,6 +4,7 @@ PyTorch is used here only for device memory (caching allocator) and the current 
 function launches hand-written sm_100a kernels from liblayoutdetr_sm100.so.  No fallbacks.
 """
 import ctypes
+import os
 from ctypes import c_void_p, c_int, c_int32, c_int64, c_float
 
 import torch
@@ -534,8 +535,22 @@ def demod_bias_act_fwd(x, d, bias, B, pixels, C, act, gain):
     return y
 
 
+DETERMINISTIC_STYLE_SUMS = os.environ.get("LD_DETERMINISTIC_STYLE_SUMS", "1") != "0"
+
+
+def _style_ws(B, pixels, C, mult, device):
+    lib().ld_style_reduce_ws_floats.restype = c_int64
+    n = int(lib().ld_style_reduce_ws_floats(c_int(B), c_int64(pixels), c_int(C)))
+    return torch.empty(mult * n, dtype=torch.float32, device=device) if n > 0 else None
+
+
 def demod_bias_act_bwd(dy, y, x, d, dd, dbias, B, pixels, C, act, gain):
     dx = torch.empty((B * pixels, C), dtype=torch.bfloat16, device=x.device)
+    ws = _style_ws(B, pixels, C, 2, x.device) if (DETERMINISTIC_STYLE_SUMS and x.dtype == torch.bfloat16) else None
+    if ws is not None:          # fixed-order sums (no fp32 atomics): run-to-run bit-identical style / bias gradients
+        check(lib().ld_demod_bias_act_bwd_ws(_p(dy), _p(y), _p(x), _p(d), _p(dx), _p(dd), _p(dbias), _p(ws), c_int64(ws.numel()), c_int(B),
+                                             c_int64(pixels), c_int(C), c_int(act), c_float(gain), _stream()), "ld_demod_bias_act_bwd_ws")
+        return dx
     check(lib().ld_demod_bias_act_bwd(_p(dy), _p(y), _p(x), c_int(dt(x)), _p(d), _p(dx), _p(dd), _p(dbias), c_int(B),
                                       c_int64(pixels), c_int(C), c_int(act), c_float(gain), _stream()), "ld_demod_bias_act_bwd")
     return dx
@@ -543,6 +558,11 @@ def demod_bias_act_bwd(dy, y, x, d, dd, dbias, B, pixels, C, act, gain):
 
 def channel_dot(a, g, B, pixels, C):
     out = torch.zeros((B, C), dtype=torch.float32, device=a.device)
+    ws = _style_ws(B, pixels, C, 1, a.device) if (DETERMINISTIC_STYLE_SUMS and a.dtype == torch.bfloat16) else None
+    if ws is not None:
+        check(lib().ld_channel_dot_ws(_p(a), _p(g), _p(out), _p(ws), c_int64(ws.numel()), c_int(B), c_int64(pixels), c_int(C), _stream()),
+              "ld_channel_dot_ws")
+        return out
     check(lib().ld_channel_dot(_p(a), c_int(dt(a)), _p(g), _p(out), c_int(B), c_int64(pixels), c_int(C), _stream()),
           "ld_channel_dot")
     return out

@@ -227,3 +227,42 @@ def test_cross_entropy_register_row_path(V, in_place):
     if Vp > V:
         pad = (buf if in_place else dbuf)[:, V:]
         assert float(pad.float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,pixels,C", [(4, 64 * 64, 128), (2, 256 * 256, 32), (3, 16 * 16, 512)])
+def test_style_gradient_reductions_are_deterministic(B, pixels, C):
+    """ld_channel_dot_ws / ld_demod_bias_act_bwd_ws (fixed-order sums through a workspace): bit-identical from run to run and equal to
+    the fp32 reference sums (reference: autograd of x * styles and of bias_act in training/networks_stylegan2.py:60-75, 307-325)."""
+    from layoutdetr_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(C + B)
+    a = torch.randn((B * pixels, C), generator=g, device="cuda").to(torch.bfloat16)
+    dy = torch.randn((B * pixels, C), generator=g, device="cuda").to(torch.bfloat16)
+    y = torch.randn((B * pixels, C), generator=g, device="cuda").to(torch.bfloat16)
+    d = torch.rand((B, C), generator=g, device="cuda") + 0.5
+    assert K.DETERMINISTIC_STYLE_SUMS
+    outs = [K.channel_dot(a, dy, B, pixels, C) for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = (a.float() * dy.float()).view(B, pixels, C).sum(1)
+    assert float((outs[0] - ref).abs().max()) < 1e-3 * float(ref.abs().max()) + 1e-3
+    runs = []
+    for _ in range(3):
+        dd = torch.zeros((B, C), device="cuda")
+        db = torch.zeros(C, device="cuda")
+        dx = K.demod_bias_act_bwd(dy, y, a, d, dd, db, B, pixels, C, K.ACT_LRELU, 2 ** 0.5)
+        runs.append((dx, dd, db))
+    for t0, t1, t2 in zip(*runs):
+        assert torch.equal(t0, t1) and torch.equal(t0, t2)
+    gact = dy.float() * (2 ** 0.5) * torch.where(y.float() < 0, 0.2, 1.0)
+    dd_ref = (gact * a.float()).view(B, pixels, C).sum(1)
+    db_ref = gact.view(B * pixels, C).sum(0)
+    dx_ref = gact.view(B, pixels, C) * d[:, None, :]
+    assert float((runs[0][1] - dd_ref).abs().max()) < 1e-3 * float(dd_ref.abs().max()) + 1e-3
+    assert float((runs[0][2] - db_ref).abs().max()) < 1e-3 * float(db_ref.abs().max()) + 1e-2
+    assert float((runs[0][0].float().view(B, pixels, C) - dx_ref).abs().max()) < 2e-2 * float(dx_ref.abs().max())
+    # the atomics forms stay available (LD_DETERMINISTIC_STYLE_SUMS=0) and agree to summation-order noise
+    K.DETERMINISTIC_STYLE_SUMS = False
+    try:
+        o2 = K.channel_dot(a, dy, B, pixels, C)
+    finally:
+        K.DETERMINISTIC_STYLE_SUMS = True
+    assert float((o2 - outs[0]).abs().max()) < 1e-3 * float(ref.abs().max()) + 1e-3

@@ -1,4 +1,9 @@
-timeout 300 python tools/gemm_probe.py > gpurun_out/r2_gemm_epilogue_variants.txt 2>&1; head -12 gpurun_out/r2_gemm_epilogue_variants.txt
-timeout 1700 python -m pytest tests -m gpu -q --timeout=900 -s > gpurun_out/r2_pytest_gpu_d.log 2>&1; tail -12 gpurun_out/r2_pytest_gpu_d.log
-timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_d.json 2> gpurun_out/r2_bench_d.err; tail -c 1500 gpurun_out/r2_bench_d.json; tail -3 gpurun_out/r2_bench_d.err
-LD_CONV_IMPLICIT=0 timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_d_explicit_conv.json 2> gpurun_out/r2_bench_d2.err; tail -c 300 gpurun_out/r2_bench_d_explicit_conv.json | head -c 100; grep -o '"value": [0-9.]*, "unit": "samples/s", "n_gpus"' gpurun_out/r2_bench_d*.json
+timeout 900 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/r2_ops python tools/ncu_ops.py > gpurun_out/r2_ncu_ops.log 2>&1; tail -2 gpurun_out/r2_ncu_ops.log
+ncu -i /tmp/r2_ops.ncu-rep --page raw --csv > gpurun_out/r2_ops_raw.csv 2>/dev/null; wc -l gpurun_out/r2_ops_raw.csv
+ncu -i /tmp/r2_ops.ncu-rep --page details > gpurun_out/r2_ops_details.txt 2>/dev/null; wc -l gpurun_out/r2_ops_details.txt
+timeout 600 ncu --set full --clock-control none -k regex:gemm_bf16 -s 6 -c 3 -f -o /tmp/r2_gemm python tools/gemm_ncu.py > gpurun_out/r2_ncu_gemm.log 2>&1; tail -2 gpurun_out/r2_ncu_gemm.log
+ncu -i /tmp/r2_gemm.ncu-rep --page raw --csv > gpurun_out/r2_gemm_raw.csv 2>/dev/null; wc -l gpurun_out/r2_gemm_raw.csv
+ncu -i /tmp/r2_gemm.ncu-rep --page details > gpurun_out/r2_gemm_details.txt 2>/dev/null
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_step_launches_ncu.csv python bench.py --ncu --graph 0 --no-cpu-baseline --variants 0 > gpurun_out/r2_ncu_launch.log 2>&1; wc -l gpurun_out/r2_step_launches_ncu.csv
+timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "deterministic" 2>&1 | tail -3
+du -sh gpurun_out
