@@ -156,6 +156,16 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization; no-ops without it):
+// pdl_trigger lets the NEXT kernel of the stream start launching, pdl_wait blocks until every kernel this one depends on has
+// completed and its writes are visible.  Pattern: trigger first, then the prologue that touches no global data (barrier init,
+// TMEM allocation, descriptor prefetch), then wait, then everything else — the prologue and the launch latency of kernel N + 1
+// run under the tail of kernel N.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
