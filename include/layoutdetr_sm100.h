@@ -86,7 +86,7 @@ typedef struct ld_gemm_desc {
     int32_t accumulate;          /* 0 store, 1 read-modify-write, 2 atomic add (required if split_k > 1) */
     int32_t split_k;             /* >= 1 */
     int32_t d_dtype, r_dtype;    /* LD_F32 / LD_BF16 */
-    int32_t block_n;             /* 0 = auto, else 128 or 256 */
+    int32_t block_n;             /* 0 = auto, else 64, 128 or 256 */
     int32_t _pad;
     float alpha, post_gain;
     ld_gemm_operand A, B;

@@ -754,7 +754,7 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
                  "gemm: split_k > 1 needs accumulate=2, fp32 output and a linear epilogue");
     LD_CHECK_ARG(d->accumulate != 2 || d->d_dtype == LD_F32, "gemm: atomic accumulation needs fp32 output");
     LD_CHECK_ARG(d->d_dtype == LD_F32 || d->d_dtype == LD_BF16, "gemm: bad d_dtype %d", d->d_dtype);
-    LD_CHECK_ARG(d->block_n == 0 || d->block_n == 128 || d->block_n == 256, "gemm: block_n must be 0/128/256");
+    LD_CHECK_ARG(d->block_n == 0 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "gemm: block_n must be 0/64/128/256");
     LD_CHECK_ARG(!d->softmax || (d->N <= 256 && d->d_dtype == LD_BF16 && d->accumulate == 0 && d->split_k == 1 && !d->aux && !d->R &&
                                  !d->col_scale && !d->col_bias && d->act == LD_ACT_NONE && d->ldd % 8 == 0 && d->d_sb1 % 8 == 0 &&
                                  d->d_sb2 % 8 == 0 && ((uintptr_t)d->D & 15) == 0),
@@ -797,6 +797,7 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     if (bn == 0) {
         const long tiles256 = nb * p.m_tiles * ceil_div(p.N, 256) * p.split_k;
         bn = (p.N > 128 && tiles256 >= sms) ? 256 : 128;
+        if (p.N <= 64) bn = 64;          // 64-channel layers (ResNet layer1, StyleGAN2 128^2): half the B fill and MMA time of a 128-wide tile
     }
     p.bn = bn;
     p.n_tiles = ceil_div(p.N, bn);

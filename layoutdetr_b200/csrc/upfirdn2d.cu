@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "runtime.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 using namespace ld;
@@ -99,6 +100,101 @@ __global__ void __launch_bounds__(256) upfirdn2d_nhwc_bf16x8_kernel(UpfirdnArgs 
         *reinterpret_cast<uint4*>(y + n * p.ysn + oy * p.ysh + ox * p.ysw + c8 * 8) = o;
     }
 }
+// Shared-memory tiled FIR for the channels-last bf16 path with up = down = 1 and filters up to 4 x 4 (the resampling filter after
+// every stride-2 transposed convolution of the StyleGAN2 synthesis network, training/networks_stylegan2.py:307-325 ->
+// torch_utils/ops/conv2d_resample.py:118-123): a block owns an 8 x 8 output tile x 32 channels.  The (8 + fh - 1) x (8 + fw - 1)
+// input tile is loaded ONCE with 128-bit loads (64 contiguous bytes per pixel), converted to fp32 ONCE and staged in shared memory;
+// a rank-1 filter (setup_filter's outer product: the only kind the path uses) is applied as a horizontal then a vertical pass,
+// 4 + 4 taps per output instead of 16; any other filter takes the 2-D loop over the same tile.  Round 1's kernel read 16 global
+// values and unpacked 16 x 8 bf16 per output (issue-bound at a quarter of the HBM peak).
+constexpr int UT = 8, UT_IN = UT + 3, UT_C = 32;
+__global__ void __launch_bounds__(256) upfirdn2d_nhwc_fir_tiled_kernel(UpfirdnArgs p, int tiles_x) {
+    __shared__ __align__(16) float tile[UT_IN * UT_IN * UT_C];      // [py][px][32 channels]
+    __shared__ __align__(16) float hbuf[UT_IN * UT * UT_C];         // [py][ox][32 channels]
+    __shared__ float sf[16], wx[4], wy[4];
+    __shared__ int sep;
+    const int t = threadIdx.x;
+    if (t < p.fh * p.fw) {
+        const int fy = t / p.fw, fx = t - fy * p.fw;
+        sf[t] = (p.flip ? p.f[t] : p.f[(p.fh - 1 - fy) * p.fw + (p.fw - 1 - fx)]) * p.gain;
+    }
+    __syncthreads();
+    if (t == 0) {
+        int ok = sf[0] != 0.f;
+        float mx = 0.f;
+        for (int i = 0; i < p.fh * p.fw; ++i) mx = fmaxf(mx, fabsf(sf[i]));
+        for (int i = 0; i < p.fh; ++i) wy[i] = sf[i * p.fw];
+        for (int j = 0; j < p.fw; ++j) wx[j] = ok ? sf[j] / sf[0] : 0.f;
+        for (int i = 0; i < p.fh && ok; ++i)
+            for (int j = 0; j < p.fw; ++j) if (fabsf(wy[i] * wx[j] - sf[i * p.fw + j]) > 1e-6f * mx) ok = 0;
+        sep = ok;
+    }
+    const int tile_id = blockIdx.x;
+    const int ty = tile_id / tiles_x, tx = tile_id - ty * tiles_x;
+    const int oy0 = ty * UT, ox0 = tx * UT;
+    const int n = blockIdx.y, c0 = blockIdx.z * UT_C;
+    const int ih = UT + p.fh - 1, iw = UT + p.fw - 1;
+    const __nv_bfloat16* x = (const __nv_bfloat16*)p.x + (long)n * p.xsn + c0;
+    // ---- input tile -> fp32 shared memory (zero outside the image: the padding of the op)
+    for (int it = t; it < ih * iw * 4; it += 256) {
+        const int c8 = it & 3, pix = it >> 2;
+        const int py = pix / iw, px = pix - py * iw;
+        const int gy = oy0 - p.pady0 + py, gx = ox0 - p.padx0 + px;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < p.inH && gx >= 0 && gx < p.inW) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (long)gy * p.xsh + (long)gx * p.xsw + c8 * 8));
+            unpack_bf16x2(a.x, v[0], v[1]); unpack_bf16x2(a.y, v[2], v[3]); unpack_bf16x2(a.z, v[4], v[5]); unpack_bf16x2(a.w, v[6], v[7]);
+        }
+        float4* dst = reinterpret_cast<float4*>(&tile[(py * UT_IN + px) * UT_C + c8 * 8]);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    const int c8 = t & 3, ox = (t >> 2) & 7, oy = t >> 5;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (sep) {
+        // horizontal pass over every input row of the tile
+        for (int it = t; it < ih * UT * 4; it += 256) {
+            const int hc8 = it & 3, hox = (it >> 2) & 7, py = it >> 5;
+            float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int fx = 0; fx < p.fw; ++fx) {
+                const float w = wx[fx];
+                const float4* src = reinterpret_cast<const float4*>(&tile[(py * UT_IN + hox + fx) * UT_C + hc8 * 8]);
+                const float4 a = src[0], b = src[1];
+                h[0] = fmaf(w, a.x, h[0]); h[1] = fmaf(w, a.y, h[1]); h[2] = fmaf(w, a.z, h[2]); h[3] = fmaf(w, a.w, h[3]);
+                h[4] = fmaf(w, b.x, h[4]); h[5] = fmaf(w, b.y, h[5]); h[6] = fmaf(w, b.z, h[6]); h[7] = fmaf(w, b.w, h[7]);
+            }
+            float4* dst = reinterpret_cast<float4*>(&hbuf[(py * UT + hox) * UT_C + hc8 * 8]);
+            dst[0] = make_float4(h[0], h[1], h[2], h[3]);
+            dst[1] = make_float4(h[4], h[5], h[6], h[7]);
+        }
+        __syncthreads();
+        for (int fy = 0; fy < p.fh; ++fy) {
+            const float w = wy[fy];
+            const float4* src = reinterpret_cast<const float4*>(&hbuf[((oy + fy) * UT + ox) * UT_C + c8 * 8]);
+            const float4 a = src[0], b = src[1];
+            acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+            acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+        }
+    } else {
+        for (int fy = 0; fy < p.fh; ++fy)
+            for (int fx = 0; fx < p.fw; ++fx) {
+                const float w = sf[fy * p.fw + fx];
+                const float4* src = reinterpret_cast<const float4*>(&tile[((oy + fy) * UT_IN + ox + fx) * UT_C + c8 * 8]);
+                const float4 a = src[0], b = src[1];
+                acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+                acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+            }
+    }
+    const int gy = oy0 + oy, gx = ox0 + ox;
+    if (gy < p.outH && gx < p.outW) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        __nv_bfloat16* y = (__nv_bfloat16*)p.y + (long)n * p.ysn + c0;
+        *reinterpret_cast<uint4*>(y + (long)gy * p.ysh + (long)gx * p.ysw + c8 * 8) = o;
+    }
+}
 }  // namespace
 
 extern "C" int ld_upfirdn2d(const void* x, void* y, int dtype, const float* f, int fh, int fw,
@@ -128,7 +224,11 @@ extern "C" int ld_upfirdn2d(const void* x, void* y, int dtype, const float* f, i
                       (((uintptr_t)x | (uintptr_t)y) & 15) == 0 &&
                       x_strides[0] % 8 == 0 && x_strides[2] % 8 == 0 && x_strides[3] % 8 == 0 &&
                       y_strides[0] % 8 == 0 && y_strides[2] % 8 == 0 && y_strides[3] % 8 == 0;
-    if (vec8) {
+    static const int env_tiled = [] { const char* e = getenv("LD_UPFIRDN_TILED"); return e ? atoi(e) : 1; }();
+    if (vec8 && env_tiled && upx == 1 && upy == 1 && downx == 1 && downy == 1 && fh <= 4 && fw <= 4 && C % UT_C == 0 && N <= 65535 && C / UT_C <= 65535) {
+        const int tiles_x = (outW + UT - 1) / UT, tiles_y = (outH + UT - 1) / UT;
+        upfirdn2d_nhwc_fir_tiled_kernel<<<dim3((unsigned)(tiles_x * tiles_y), (unsigned)N, (unsigned)(C / UT_C)), 256, 0, (cudaStream_t)stream>>>(p, tiles_x);
+    } else if (vec8) {
         const long tv = total / 8;
         const int gv = (int)std::max<long>(1, std::min<long>((tv + 255) / 256, (long)ld::sm_count() * 16));
         upfirdn2d_nhwc_bf16x8_kernel<<<gv, 256, 0, (cudaStream_t)stream>>>(p);

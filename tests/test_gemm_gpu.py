@@ -36,7 +36,7 @@ def test_gemm_majors(M, N, K, a_mn, b_mn):
     _check(D, ref, what="gemm M%d N%d K%d a_mn=%s b_mn=%s" % (M, N, K, a_mn, b_mn))
 
 
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
 def test_gemm_epilogue(block_n):
     from layoutdetr_b200 import kernels as k
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -184,3 +184,27 @@ def test_gemm_fused_softmax_epilogue(Lq, Lk, d, H, mask_inf, causal):
     torch.testing.assert_close(P[:, :, :Lk].float(), ref, atol=4e-3, rtol=2e-2)
     if Lkp > Lk:
         assert float(P[:, :, Lk:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("N", [64, 40, 24])
+def test_gemm_narrow_n_takes_the_64_wide_tile(N, a_mn, b_mn):
+    """N <= 64 (64-channel convolution layers, narrow heads): the 128 x 64 tile (UMMA N = 64) in every operand-major form, fast bf16
+    epilogue with bias + ReLU and the fp32 accumulate path."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(N + 7)
+    M, K = 1000, 200
+    A, B = _rand((M, K), g, 0.5), _rand((N, K), g, 0.5)
+    At = A.t().contiguous() if a_mn else A
+    Bt = B.t().contiguous() if b_mn else B
+    if b_mn and N % 8:
+        pytest.skip("MN-major operands need a leading dimension that is a multiple of 8")
+    bias = torch.randn(N, generator=g, device="cuda")
+    ref = A.float() @ B.float().t()
+    D = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    k.gemm(M, N, K, k.Op(At, At.stride(0), mn=a_mn), k.Op(Bt, Bt.stride(0), mn=b_mn), k.Out(D, N), act=k.ACT_RELU, col_bias=bias)
+    acc = torch.ones((M, N), dtype=torch.float32, device="cuda")
+    k.gemm(M, N, K, k.Op(At, At.stride(0), mn=a_mn), k.Op(Bt, Bt.stride(0), mn=b_mn), k.Out(acc, N), accumulate=1)
+    torch.cuda.synchronize()
+    _check(D, torch.relu(ref + bias), tol=1e-2, what="narrow N=%d" % N)
+    _check(acc, ref + 1.0, tol=1e-2, what="narrow N=%d accumulate" % N)

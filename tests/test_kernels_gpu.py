@@ -266,3 +266,34 @@ def test_style_gradient_reductions_are_deterministic(B, pixels, C):
     finally:
         K.DETERMINISTIC_STYLE_SUMS = True
     assert float((o2 - outs[0]).abs().max()) < 1e-3 * float(ref.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("B,H,C,sep", [(2, 33, 32, True), (1, 129, 64, True), (3, 17, 512, True), (2, 21, 32, False)])
+def test_upfirdn_nhwc_tiled_fir_matches_reference(B, H, C, sep):
+    """The shared-memory tiled FIR (up = down = 1, channels-last bf16: the filter after a stride-2 transposed convolution,
+    training/networks_stylegan2.py:307-325) vs the oracle's restatement of _upfirdn2d_ref (torch_utils/ops/upfirdn2d.py:168-214)
+    on the same bf16-rounded input — rank-1 filter (two 1-D passes) and a non-separable filter (2-D loop), values and the
+    backward pass (another upfirdn2d with the flipped filter)."""
+    from layoutdetr_b200 import functional as Fn
+    from oracle import layoutdetr_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + C)
+    x = torch.randn((B * H * H, C), generator=g, device="cuda").to(torch.bfloat16)
+    f1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    f = torch.outer(f1, f1)
+    if not sep:
+        f = f + torch.tensor([[0.0, 0.5, 0.0, 0.0], [0.0, 0.0, 0.0, 0.25], [0.3, 0.0, 0.0, 0.0], [0.0, 0.0, 0.1, 0.0]])
+    f = (f / f.sum()).cuda()
+    xi = x.clone().requires_grad_(True)
+    y = Fn.upfirdn_nhwc(xi, f, B, H, H, pad=(1, 1, 1, 1), gain=4.0)
+    oh = H - 1
+    dy = torch.randn((B * oh * oh, C), generator=g, device="cuda").to(torch.bfloat16)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    x4 = x.float().cpu().view(B, H, H, C).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = O.upfirdn2d(x4, f.cpu(), padding=(1, 1, 1, 1), gain=4.0)
+    ref.backward(dy.float().cpu().view(B, oh, oh, C).permute(0, 3, 1, 2))
+    y_ref = ref.detach().permute(0, 2, 3, 1).reshape(B * oh * oh, C)
+    dx_ref = x4.grad.permute(0, 2, 3, 1).reshape(B * H * H, C)
+    assert tuple(y.shape) == tuple(y_ref.shape)
+    assert float((y.float().cpu() - y_ref).abs().max()) < 1e-2 * float(y_ref.abs().max())
+    assert float((xi.grad.float().cpu() - dx_ref).abs().max()) < 1e-2 * float(dx_ref.abs().max())

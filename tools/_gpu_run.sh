@@ -1,4 +1,5 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571"
-timeout 600 $TR bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2_driver_flags.json 2> gpurun_out/r2_bench_n2_driver_flags.err; echo "rc=$?"; grep "^{" gpurun_out/r2_bench_n2_driver_flags.json | tail -c 1800; tail -4 gpurun_out/r2_bench_n2_driver_flags.err
-timeout 300 $TR bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/r2_bench_n2_ref.json 2> gpurun_out/r2_bench_n2_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/r2_bench_n2_ref.json
-timeout 600 python -m pytest tests/test_dp_gpu.py -m gpu -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_conv_implicit_gpu.py tests/test_kernels_gpu.py tests/test_stylegan2_gpu.py -m gpu -q --timeout=600 2>&1 | tail -12
+LD_UPFIRDN_TILED=0 timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_f_untiled.json 2> gpurun_out/r2_bench_f.err
+timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_f.json 2> gpurun_out/r2_bench_f.err
+grep -o '"value": [0-9.]*, "unit": "samples/s", "n_gpus": 1, "steps": 10, "warmup": 3, "ms_per_step": [0-9.]*' gpurun_out/r2_bench_f*.json; tail -3 gpurun_out/r2_bench_f.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_step_launches_ncu.csv python bench.py --ncu --graph 0 --no-cpu-baseline --variants 0 > gpurun_out/r2_ncu_launch.log 2>&1; wc -l gpurun_out/r2_step_launches_ncu.csv
