@@ -405,10 +405,17 @@ def run_ours(args):
     sync_all()
 
     if args.ncu:                                            # one profiled step: ncu --profile-from-start off
+        log_path = os.environ.get("LD_GEMM_LOG")            # also dump (M, N, K, ...) of every GEMM of that step, in launch order
+        if log_path:
+            K.GEMM_LOG = []
         torch.cuda.profiler.start()
         step_resident()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        if log_path:
+            with open(log_path, "w") as f:
+                json.dump([[e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8].get("act"), e[8].get("d_dtype"), bool(e[8].get("r")),
+                            bool(e[8].get("conv"))] for e in K.GEMM_LOG], f)
         return
 
     # ---- timed: resident inputs

@@ -786,8 +786,13 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     // (profiles/r1_bench_n1_gemm_2sm.json vs r1_bench_n1.json, same box, back to back).
     static const int env_2sm = [] { const char* e = getenv("LD_GEMM_2SM"); return e ? atoi(e) : 1; }();
     const long nb_ = (long)d->nb1 * d->nb2;
-    const bool two_sm = env_2sm && d->block_n != 128 && d->N > 128 && d->M >= 256 && !d->softmax &&
-                        nb_ * ceil_div(d->M, 256) * ceil_div(d->N, 256) * d->split_k >= (sms / 2);
+    // threshold 3/8 of the SMs in pairs (55 of 74): the LM-decoder weight gradients (768 x 768 and 768 x 3072 outputs, split-K 8 / 2)
+    // have 72 pair tiles — as 288 single-CTA 128 x 128 tiles they ran fill-bound at 480-670 TFLOP/s (profiles/r2_gemm_time_by_shape.txt)
+    // (with short reductions the pair kernel's longer prologue costs 1-2 us, so the lower threshold applies from 32 K blocks per split)
+    const long k_blocks_per_split = ceil_div(ceil_div(d->K, BK), d->split_k);
+    const long pair_min = k_blocks_per_split >= 32 ? (sms * 3 / 8) : (sms / 2);
+    const bool two_sm = env_2sm && d->block_n != 128 && d->block_n != 64 && d->N > 128 && d->M >= 256 && !d->softmax &&
+                        nb_ * ceil_div(d->M, 256) * ceil_div(d->N, 256) * d->split_k >= pair_min;
     p.tile_m = two_sm ? 256 : BM;
     p.m_tiles = ceil_div(p.M, p.tile_m);
     const long nb = (long)p.nb1 * p.nb2;
@@ -826,6 +831,14 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     if (p.aux && !aligned(p.aux, p.ldd, p.d_sb1, p.d_sb2, d_es)) p.vec_ok = 0;
     if (p.R && !aligned(p.R, p.ldr, p.r_sb1, p.r_sb2, p.r_dtype == LD_BF16 ? 2 : 4)) p.vec_ok = 0;
 
+    // fp32 read-modify-write (weight gradients accumulated straight into .grad) = the fp32-residual epilogue with R aliased to D:
+    // every lane of a warp reads its row's chunk before any lane stores (the stores go through the warp's transpose buffer after a
+    // __syncwarp), and warps own disjoint rows / columns — so the vectorised fast path serves it (the generic path took ~2x as long
+    // on the DETR-sized weight gradients, 230 launches per iteration).
+    if (p.accumulate == 1 && p.d_dtype == LD_F32 && !p.R && !p.aux && p.act == LD_ACT_NONE && p.post_gain == 1.0f && p.vec_ok) {
+        p.R = p.D; p.r_dtype = LD_F32; p.ldr = p.ldd; p.r_sb1 = p.d_sb1; p.r_sb2 = p.d_sb2;
+        p.accumulate = 0;
+    }
     // fast epilogue: vector stores, plain store, no aux; activations only with bf16 output and non-fp32 residual
     p.fast = (p.vec_ok && p.accumulate == 0 && !p.aux &&
               (p.act == LD_ACT_NONE || (p.d_dtype == LD_BF16 && !(p.R && p.r_dtype == LD_F32)))) ? 1 : 0;

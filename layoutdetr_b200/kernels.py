@@ -126,7 +126,8 @@ def gemm(M, N, K, A, B, D, nb1=1, nb2=1, alpha=1.0, act=ACT_NONE, post_gain=1.0,
                          dict(nb1=nb1, nb2=nb2, alpha=alpha, act=act, post_gain=post_gain, accumulate=accumulate, d_dtype=str(D.t.dtype),
                               ldd=D.ld, d_sb=(D.sb1, D.sb2), a_ld=A.ld, a_sb=(A.sb1, A.sb2), b_ld=B.ld, b_sb=(B.sb1, B.sb2),
                               r=None if R is None else (str(R.t.dtype), R.ld), cs=col_scale is not None, cb=col_bias is not None,
-                              aux=aux is not None, block_n=block_n, alpha_dev=alpha_dev is not None, softmax=softmax is not None)))
+                              aux=aux is not None, block_n=block_n, alpha_dev=alpha_dev is not None, softmax=softmax is not None,
+                              conv=None if conv is None else conv["mode"])))
     d = _GemmDesc()
     d.M, d.N, d.K, d.nb1, d.nb2 = M, N, K, nb1, nb2
     d.act, d.accumulate, d.split_k = act, accumulate, split_k

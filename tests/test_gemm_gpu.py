@@ -208,3 +208,20 @@ def test_gemm_narrow_n_takes_the_64_wide_tile(N, a_mn, b_mn):
     torch.cuda.synchronize()
     _check(D, torch.relu(ref + bias), tol=1e-2, what="narrow N=%d" % N)
     _check(acc, ref + 1.0, tol=1e-2, what="narrow N=%d accumulate" % N)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 160), (296, 200, 144), (768, 768, 4096), (2048, 256, 160)])
+def test_gemm_fp32_accumulate_fast_path(M, N, K):
+    """Weight-gradient form (both operands MN-major) accumulated into an fp32 buffer (accumulate = 1): served by the vectorised
+    epilogue with the residual aliased to the output; tails in M and N, a device-side alpha, two accumulations in a row."""
+    from layoutdetr_b200 import kernels as k
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    At, Bt = _rand((K, M), g, 0.5), _rand((K, N), g, 0.5)
+    base = torch.randn((M, N), generator=g, device="cuda")
+    D = base.clone()
+    alpha_dev = torch.tensor([0.5], device="cuda")
+    k.gemm(M, N, K, k.Op(At, M, mn=True), k.Op(Bt, N, mn=True), k.Out(D, N), accumulate=1, alpha_dev=alpha_dev)
+    k.gemm(M, N, K, k.Op(At, M, mn=True), k.Op(Bt, N, mn=True), k.Out(D, N), accumulate=1)
+    torch.cuda.synchronize()
+    prod = At.float().t() @ Bt.float()
+    _check(D, base + 1.5 * prod, tol=5e-3, what="fp32 accumulate M%d N%d K%d" % (M, N, K))

@@ -1,5 +1,2 @@
-timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_conv_implicit_gpu.py tests/test_kernels_gpu.py tests/test_stylegan2_gpu.py -m gpu -q --timeout=600 2>&1 | tail -12
-LD_UPFIRDN_TILED=0 timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_f_untiled.json 2> gpurun_out/r2_bench_f.err
-timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_f.json 2> gpurun_out/r2_bench_f.err
-grep -o '"value": [0-9.]*, "unit": "samples/s", "n_gpus": 1, "steps": 10, "warmup": 3, "ms_per_step": [0-9.]*' gpurun_out/r2_bench_f*.json; tail -3 gpurun_out/r2_bench_f.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_step_launches_ncu.csv python bench.py --ncu --graph 0 --no-cpu-baseline --variants 0 > gpurun_out/r2_ncu_launch.log 2>&1; wc -l gpurun_out/r2_step_launches_ncu.csv
+timeout 300 python tools/splitk_probe.py > gpurun_out/r2_splitk_probe.txt 2>&1; cat gpurun_out/r2_splitk_probe.txt
+timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q --timeout=600 2>&1 | tail -3
