@@ -240,10 +240,29 @@ def grad_writes_done():
 
 
 def wgrad_split_k(M_out, N_out, K_red):
-    """Split-K factor for weight-gradient GEMMs (few output tiles, long reduction)."""
-    tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
+    """Split-K factor for weight-gradient GEMMs (few output tiles, long reduction; partial sums meet through fp32 atomics).
+
+    Cost model fitted to the B200 sweep in profiles/r2_splitk_probe.txt (both operands MN-major): a CTA spends ~0.43 us per
+    64-deep K block on a 128 x 128 tile (a CTA pair ~0.40 us on its 256 x 256 tile), a launch costs ~5 us, and the atomic adds
+    of all splits drain at ~160 G fp32 atomics / s — the best factor balances the K loop against sk * M * N atomics.  (The
+    round-1 rule "fill 2 x the SMs" over-split small outputs: 256 x 64 x 65536 ran 148 splits in 40 us, 32 splits take 20 us;
+    512 x 4608 x 1024 ran 2 splits in 34 us, one takes 15 us.)"""
     kb = (K_red + 63) // 64
     sms = sm_count()
-    if tiles >= sms or kb <= 8:
-        return 1
-    return int(max(1, min(kb // 4, (2 * sms) // tiles)))
+    tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
+    pairs = ((M_out + 255) // 256) * ((N_out + 255) // 256)
+    pair_ok = M_out >= 256 and N_out > 128
+    best, best_cost = 1, None
+    for sk in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128):
+        if sk > max(1, kb // 2):
+            break
+        per_split = -(-kb // sk)
+        if pair_ok and pairs * sk >= (sms * 3 // 8 if per_split >= 32 else sms // 2):      # gemm_sm100.cu takes the CTA-pair kernel
+            loop = (-(-(pairs * sk) // (sms // 2))) * per_split * 0.40
+        else:
+            loop = (-(-(tiles * sk) // sms)) * per_split * 0.43
+        atomics = 0.0 if sk == 1 else sk * M_out * N_out / 160000.0
+        cost = 5.0 + loop + atomics
+        if best_cost is None or cost < best_cost * 0.97:        # prefer fewer splits on near ties
+            best, best_cost = sk, cost
+    return best
