@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_train_gpu.py tests/test_stylegan2_gpu.py tests/test_conv_implicit_gpu.py tests/test_graph_gpu.py -m gpu -q --timeout=900 2>&1 | tail -4
-timeout 600 python bench.py --no-cpu-baseline --variants 0 --loop-steps 0 > gpurun_out/r2_bench_h.json 2> gpurun_out/r2_bench_h.err
-grep -o '"value": [0-9.]*, "unit": "samples/s", "n_gpus": 1, "steps": 10, "warmup": 3, "ms_per_step": [0-9.]*' gpurun_out/r2_bench_h.json; tail -3 gpurun_out/r2_bench_h.err
-LD_GEMM_LOG=gpurun_out/r2_gemm_log.json timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_step_launches_ncu.csv python bench.py --ncu --graph 0 --no-cpu-baseline --variants 0 > gpurun_out/r2_ncu_launch.log 2>&1; wc -l gpurun_out/r2_step_launches_ncu.csv
+timeout 1700 python -m pytest tests -m gpu -q --timeout=900 > gpurun_out/r2_pytest_gpu_final.log 2>&1; tail -6 gpurun_out/r2_pytest_gpu_final.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench rc=$?"; grep "^{" gpurun_out/r2_bench_final.json | tail -c 2600; tail -3 gpurun_out/r2_bench_final.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/r2_bench_ref.json 2> gpurun_out/r2_bench_ref.err; echo "ref rc=$?"; tail -c 700 gpurun_out/r2_bench_ref.json
