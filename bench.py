@@ -47,7 +47,7 @@ def bench_loop(args, dev, B, world, rank):
     net = lambda kw, cls: dict({k: v for k, v in kw.items() if k not in common}, class_name="layoutdetr_b200.training.networks_detr." + cls)
     ds = dict(class_name="layoutdetr_b200.training.synthetic_dataset.SyntheticLayoutDataset", num_items=4096, n_valid=8, seed=rank)
     marks = {}
-    W, K = max(3, args.warmup), args.steps
+    W, K = max(3, args.warmup), max(20, args.steps)        # wall-clock window: at least 20 iterations (10 are within +-2 % run to run)
 
     def cb(i):
         if i == W or i == W + K:

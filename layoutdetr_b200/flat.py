@@ -51,7 +51,13 @@ class FlatParams:
     def set_hyper(self, lr, beta1, beta2):
         """Advance the step counter and publish the step-dependent scalars on the device (outside any graph capture)."""
         self.step += 1
-        self.hyper.copy_(torch.tensor([lr, 1.0 - beta1 ** self.step, 1.0 - beta2 ** self.step], dtype=torch.float32))
+        h = torch.tensor([lr, 1.0 - beta1 ** self.step, 1.0 - beta2 ** self.step], dtype=torch.float32)
+        if self.hyper.is_cuda:
+            # pinned source + asynchronous copy: the host must not wait for the previous replay here (a fresh pinned tensor per
+            # call — the caching host allocator keeps it alive until the copy has run)
+            self.hyper.copy_(h.pin_memory(), non_blocking=True)
+        else:
+            self.hyper.copy_(h)
 
     def adam_step(self, lr, beta1, beta2, eps, grad_scale=1.0):
         if not torch.cuda.is_current_stream_capturing():

@@ -266,13 +266,18 @@ def training_loop(
     if progress_fn is not None:
         progress_fn(0, total_kimg)
     pending = first
+    host_prof = [] if os.environ.get('LD_LOOP_PROFILE') else None       # host wall time per phase of an iteration (ms): fetch, pin, z, run
     while True:
         # Fetch training data (host side: pinned tensors + strings; the H2D copies go into the graph's static buffers).
+        t_h0 = time.perf_counter()
         if pending is not None:
             batch, pending = pending, None
+            t_h1 = time.perf_counter()
         else:
             samples, real_c = next(training_set_iterator)
+            t_h1 = time.perf_counter()
             batch = fetch_batch(samples, real_c)
+        t_h2 = time.perf_counter()
         N = batch['bbox_real'].shape[1]
         all_gen_z = torch.randn([n_phases * batch_size, N, G.z_dim], dtype=torch.float32, device=device)     # same draw as :267
         phase_z = [zz[:per_rank] for zz in all_gen_z.split(batch_size)]                                       # one slice per phase
@@ -281,6 +286,7 @@ def training_loop(
             np.random.randint(len(training_set))
 
         # Execute training phases: Gmain (+ Greg no-op) + Dmain (+ Dreg no-op) + both optimizer steps + G_ema.
+        t_h3 = time.perf_counter()
         iter_ev[0].record(torch.cuda.current_stream(device))
         if graphed is not None:
             graphed.run(batch, z_g, z_d)
@@ -292,6 +298,9 @@ def training_loop(
             else:
                 trainer.iteration_multi(dev_micro, list(z_g.split(batch_gpu)), list(z_d.split(batch_gpu)))
         iter_ev[1].record(torch.cuda.current_stream(device))
+        if host_prof is not None:
+            t_h4 = time.perf_counter()
+            host_prof.append((t_h1 - t_h0, t_h2 - t_h1, t_h3 - t_h2, t_h4 - t_h3))
 
         # Update state.
         cur_nimg += batch_size
@@ -393,6 +402,10 @@ def training_loop(
 
     if stats_jsonl is not None:
         stats_jsonl.close()
+    if host_prof and rank == 0:
+        tail = host_prof[len(host_prof) // 2:]
+        print('host ms per iteration (second half of the run): next(loader) %.2f | fetch_batch (pin) %.2f | z / bookkeeping %.2f | run (tokenise, H2D, replay launch) %.2f'
+              % tuple(1e3 * sum(t[i] for t in tail) / len(tail) for i in range(4)))
     if graphed is not None and num_gpus > 1:
         graphed.close()              # graphs holding captured NCCL collectives must be gone before the process group is torn down
     if rank == 0:
