@@ -112,7 +112,8 @@ int ld_gemm_bf16(const ld_gemm_desc* desc, void* stream);
  * neighbours and of the StyleGAN2 synthesis 3x3 layers (training/networks_stylegan2.py:30-83), forward, data gradient and weight
  * gradient, WITHOUT a patch matrix in HBM: the TMA producer loads boxes of output pixels x 64 channels straight from the NHWC
  * bf16 image at the tap's offset (out-of-image taps are zero-filled by the TMA unit; the convolution stride is the tensor map's
- * traversal stride).  `img` is [B, H, W, C] bf16 contiguous, C % 64 == 0; Ho = (H + 2 pad - KH) / stride + 1 (same for W);
+ * traversal stride).  `img` is [B, H, W, C] bf16 contiguous, C % 64 == 0 (mode 1 also takes C == 32: K blocks of 32 channels in
+ * 64-byte-swizzled rows, weight matrix K-major, split_k = 1); Ho = (H + 2 pad - KH) / stride + 1 (same for W);
  * a box of `mode == 1 ? 128 : 64` consecutive output pixels must be a rectangle of whole rows / whole images
  * (Wo % box == 0, or box % Wo == 0 with Ho*Wo % box == 0 or box % (Ho*Wo) == 0) — LD_ERR_INVALID_ARG otherwise.
  *   mode 1 (forward, and data gradient as a convolution of dy with the flipped, transposed weights):

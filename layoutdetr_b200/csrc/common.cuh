@@ -397,6 +397,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
+// Same for a K-major tile of 64-byte rows (32 bf16 per row, SWIZZLE_64B: layout type 4; 8-row groups 512 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((16u >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulation.
 //   c_format [4,6)=1 (f32)  a_format [7,10)=1 (bf16)  b_format [10,13)=1 (bf16)
 //   a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)

@@ -59,6 +59,7 @@ struct KParams {
     int softmax, causal; float mask_value; const uint8_t* key_mask;
     // implicit-GEMM convolution (ld_conv_gemm_bf16): 0 off, 1 = A rows are output pixels, 2 = B (MN-major) rows are output pixels
     int cv_mode, cv_P, cv_Wo, cv_stride, cv_pad, cv_KW, cv_C;
+    int k32;         // K blocks of 32 (64-byte rows, SWIZZLE_64B): implicit convolution over 32-channel images (mode 1, single-CTA kernel)
 };
 
 // First output pixel of a box -> TMA coordinates (w, h, b) of tap (kh, kw) in the NHWC image.
@@ -483,7 +484,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const int b_rows = TWO_SM ? (p.bn >> 1) : p.bn;           // B rows this CTA stages per k-block
-            const uint32_t tx_bytes = (TWO_SM ? 2u : 1u) * (A_STAGE_BYTES + b_rows * BK * 2);
+            const int bk = p.k32 ? 32 : BK;
+            const uint32_t tx_bytes = (TWO_SM ? 2u : 1u) * (BM * bk * 2 + b_rows * bk * 2);
             for (int t = unit; t < p.total_tiles; t += nunits) {
                 const Tile tl = decode_tile(p, t);
                 const int am0 = tl.m0 + (int)rank * BM;
@@ -493,7 +495,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                     uint8_t* sa = smem + stage * SBYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    const int k0 = kb * BK;
+                    const int k0 = kb * bk;
                     if (p.cv_mode == 1) {
                         // K block -> (tap, channel block); the A tile is a box of 128 output pixels x 64 channels of the image
                         const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
@@ -553,6 +555,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * SBYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
+                    if (p.k32) {                      // 64-byte rows: two UMMA_K steps per K block
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t acc = (kb > tl.kb_begin || k > 0) ? 1u : 0u;
+                            umma_bf16_ss(tmem_d, make_smem_desc_sw64(sa + k * 32), make_smem_desc_sw64(sb + k * 32), idesc, acc);
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major: 32 B per UMMA_K step inside the 128 B swizzle row; 8-row groups 1024 B apart.
@@ -668,7 +677,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     gemm_body<true>(tmA, tmB, p);
 }
 
-int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K, int nb1, int nb2, int box_rows) {
+int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K, int nb1, int nb2, int box_rows, bool k32 = false) {
     if (!op.ptr) { set_last_error("gemm: null operand"); return LD_ERR_INVALID_ARG; }
     if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) != 0) { set_last_error("gemm: operand pointer %p not 16-byte aligned", op.ptr); return LD_ERR_ALIGNMENT; }
     if (op.ld % 8 != 0 || (nb2 > 1 && op.sb2 % 8 != 0) || (nb1 > 1 && op.sb1 % 8 != 0)) {
@@ -687,6 +696,7 @@ int make_operand_map(CUtensorMap* tm, const ld_gemm_operand& op, int rows, int K
     if (outer == 1 && strides[0] == 0) strides[0] = dummy;
     for (int i = 0; i < 3; ++i) if (strides[i] == 0) { set_last_error("gemm: zero stride for a batched dimension"); return LD_ERR_INVALID_ARG; }
     const uint32_t box_outer = op.mn_major ? (uint32_t)BK : (uint32_t)box_rows;
+    if (k32) return encode_tmap_bf16_4d(tm, op.ptr, dims, strides, 32, box_outer, 64);       // K-major, 32-deep K blocks
     return encode_tmap_bf16_4d(tm, op.ptr, dims, strides, 64, box_outer);
 }
 
@@ -698,7 +708,8 @@ namespace {
 int make_conv_map(CUtensorMap* tm, const ld_conv_geom& g, int pix) {
     using namespace ld;
     if (!g.img || (reinterpret_cast<uintptr_t>(g.img) & 15) != 0) { set_last_error("conv gemm: image pointer null or not 16-byte aligned"); return LD_ERR_ALIGNMENT; }
-    if (g.C % 64 != 0 || g.C <= 0) { set_last_error("conv gemm: C = %d must be a positive multiple of 64", g.C); return LD_ERR_INVALID_ARG; }
+    const bool c32 = g.C == 32 && g.mode == 1;
+    if ((g.C % 64 != 0 && !c32) || g.C <= 0) { set_last_error("conv gemm: C = %d must be a positive multiple of 64 (or 32 in mode 1)", g.C); return LD_ERR_INVALID_ARG; }
     if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.KH <= 0 || g.KW <= 0 || g.stride <= 0 || g.pad < 0) { set_last_error("conv gemm: bad geometry"); return LD_ERR_INVALID_ARG; }
     if (g.Ho != (g.H + 2 * g.pad - g.KH) / g.stride + 1 || g.Wo != (g.W + 2 * g.pad - g.KW) / g.stride + 1 || g.Ho <= 0 || g.Wo <= 0) {
         set_last_error("conv gemm: Ho x Wo = %d x %d inconsistent with H x W = %d x %d, k = %d x %d, stride %d, pad %d", g.Ho, g.Wo, g.H, g.W, g.KH, g.KW, g.stride, g.pad);
@@ -717,9 +728,9 @@ int make_conv_map(CUtensorMap* tm, const ld_conv_geom& g, int pix) {
     {
         const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
         const uint64_t strides[3] = {(uint64_t)g.C * 2, (uint64_t)g.W * g.C * 2, (uint64_t)g.H * g.W * g.C * 2};
-        const uint32_t box[4] = {64u, (uint32_t)(bw * g.stride), (uint32_t)(bh * g.stride), (uint32_t)bb};
+        const uint32_t box[4] = {c32 ? 32u : 64u, (uint32_t)(bw * g.stride), (uint32_t)(bh * g.stride), (uint32_t)bb};
         const uint32_t estr[4] = {1u, (uint32_t)g.stride, (uint32_t)g.stride, 1u};
-        return encode_tmap_bf16_4d_box(tm, g.img, dims, strides, box, estr);
+        return encode_tmap_bf16_4d_box(tm, g.img, dims, strides, box, estr, c32 ? 64 : 128);
     }
 bad:
     set_last_error("conv gemm: a box of %d output pixels is not a rectangle of whole rows / images for Ho x Wo = %d x %d (stride %d)", pix, g.Ho, g.Wo, g.stride);
@@ -776,6 +787,7 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
         p.cv_mode = cg->mode; p.cv_P = cg->Ho * cg->Wo; p.cv_Wo = cg->Wo; p.cv_stride = cg->stride; p.cv_pad = cg->pad;
         p.cv_KW = cg->KW; p.cv_C = cg->C;
         if (cg->mode == 1) p.a_mn = 0; else p.b_mn = 1;
+        p.k32 = (cg->mode == 1 && cg->C == 32) ? 1 : 0;
     }
 
     const int sms = sm_count();
@@ -791,7 +803,7 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     // (with short reductions the pair kernel's longer prologue costs 1-2 us, so the lower threshold applies from 32 K blocks per split)
     const long k_blocks_per_split = ceil_div(ceil_div(d->K, BK), d->split_k);
     const long pair_min = k_blocks_per_split >= 32 ? (sms * 3 / 8) : (sms / 2);
-    const bool two_sm = env_2sm && d->block_n != 128 && d->block_n != 64 && d->N > 128 && d->M >= 256 && !d->softmax &&
+    const bool two_sm = env_2sm && !p.k32 && d->block_n != 128 && d->block_n != 64 && d->N > 128 && d->M >= 256 && !d->softmax &&
                         nb_ * ceil_div(d->M, 256) * ceil_div(d->N, 256) * d->split_k >= pair_min;
     p.tile_m = two_sm ? 256 : BM;
     p.m_tiles = ceil_div(p.M, p.tile_m);
@@ -806,7 +818,7 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     }
     p.bn = bn;
     p.n_tiles = ceil_div(p.N, bn);
-    p.kb_total = ceil_div(p.K, BK);
+    p.kb_total = ceil_div(p.K, p.k32 ? 32 : BK);
     if (p.split_k > p.kb_total) p.split_k = p.kb_total;
     p.kb_per_split = ceil_div(p.kb_total, p.split_k);
     p.split_k = ceil_div(p.kb_total, p.kb_per_split);     // no empty splits
@@ -849,7 +861,8 @@ int gemm_launch(const ld_gemm_desc* d, const ld_conv_geom* cg, void* stream) {
     alignas(64) CUtensorMap tmA, tmB;
     int e = (cg && cg->mode == 1) ? make_conv_map(&tmA, *cg, BM) : make_operand_map(&tmA, d->A, p.M, p.K, p.nb1, p.nb2, BM);
     if (e) return e;
-    e = (cg && cg->mode == 2) ? make_conv_map(&tmB, *cg, BK) : make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, two_sm ? bn / 2 : bn);
+    if (p.k32) LD_CHECK_ARG(!p.b_mn && p.split_k == 1, "conv gemm: 32-channel images need a K-major weight matrix and split_k = 1");
+    e = (cg && cg->mode == 2) ? make_conv_map(&tmB, *cg, BK) : make_operand_map(&tmB, d->B, p.N, p.K, p.nb1, p.nb2, two_sm ? bn / 2 : bn, p.k32 != 0);
     if (e) return e;
 
     static bool attr_set = false;

@@ -73,7 +73,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                        uint32_t box_inner, uint32_t box_outer) {
+                        uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
     // cuTensorMapEncodeTiled is a driver entry point: it needs the primary context bound to THIS thread (autograd runs
     // backward on worker threads that may not have issued a runtime call yet).
     static thread_local bool ctx_bound = false;
@@ -85,8 +85,8 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4
     cuuint32_t box[4] = {box_inner, box_outer, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u]",
                        (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
@@ -100,7 +100,7 @@ int encode_tmap_bf16_4d(CUtensorMap* out, const void* ptr, const uint64_t dims[4
 // General form: explicit box and traversal strides per dimension (implicit-GEMM convolution: a box of output pixels over an
 // NHWC image, elementStrides = the convolution stride on W / H).
 int encode_tmap_bf16_4d_box(CUtensorMap* out, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                            const uint32_t box[4], const uint32_t estr[4]) {
+                            const uint32_t box[4], const uint32_t estr[4], int swizzle_bytes) {
     static thread_local bool ctx_bound = false;
     if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
     EncodeTiledFn fn = get_encode_fn();
@@ -110,8 +110,8 @@ int encode_tmap_bf16_4d_box(CUtensorMap* out, const void* ptr, const uint64_t di
     cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
     cuuint32_t e[4] = {estr[0], estr[1], estr[2], estr[3]};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, b, e,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u] estr=[%u,%u,%u,%u]",
                        (int)r, ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],

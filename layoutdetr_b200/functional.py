@@ -600,7 +600,8 @@ class Conv2dFn(_Fn):
     """y = act(conv(x, W) * scale + shift + residual) on channels-last bf16 activations.
 
     Implicit GEMM (ld_conv_gemm_bf16: the TMA producer reads boxes of pixels x 64 channels straight from the NHWC image, no
-    patch matrix in HBM) whenever the channel count is a multiple of 64 and a box of output pixels is a rectangle of whole rows —
+    patch matrix in HBM) whenever the channel count is a multiple of 64 (or exactly 32: 64-byte-swizzle K blocks, forward and data
+    gradient) and a box of output pixels is a rectangle of whole rows —
     forward, the stride-1 data gradient (a convolution of dy with the flipped, transposed weights) and the weight gradient;
     the 3-channel stem and odd geometries keep the explicit im2col / col2im path.
 
@@ -619,7 +620,7 @@ class Conv2dFn(_Fn):
         out = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
         epi = dict(act=act, R=K.Out(residual, residual.stride(0)) if residual is not None else None,
                    col_scale=scale, col_bias=shift.detach() if shift is not None else None)
-        implicit = (not direct and IMPLICIT_CONV and Cin % 64 == 0 and x.is_contiguous() and K.conv_box_ok(Ho, Wo, stride, 128))
+        implicit = (not direct and IMPLICIT_CONV and (Cin % 64 == 0 or Cin == 32) and x.is_contiguous() and K.conv_box_ok(Ho, Wo, stride, 128))
         if implicit:
             K.gemm(M, Cout, KH * KW * Cin, K.Op(x, Cin), K.Op(w16, w16.stride(0)), K.Out(out, Cout),
                    conv=_conv_geom(x, 1, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad), **epi)
@@ -660,7 +661,7 @@ class Conv2dFn(_Fn):
         dconv = dconv.contiguous()
         if ctx.needs_input_grad[0]:
             same = stride == 1 and Ho == H and Wo == W and KH == KW
-            if (not direct and IMPLICIT_CONV and same and Cout % 64 == 0 and K.conv_box_ok(H, W, 1, 128)):
+            if (not direct and IMPLICIT_CONV and same and (Cout % 64 == 0 or Cout == 32) and K.conv_box_ok(H, W, 1, 128)):
                 # dx = conv(dy, flipped weights), pad' = k - 1 - pad: no [M, 9 Cin] temporary, no col2im pass
                 wf = conv_weight_flipT_bf16(weight)
                 dx = torch.empty((B * H * W, Cin), dtype=torch.bfloat16, device=x.device)

@@ -19,6 +19,9 @@ CASES = [
     (1, 128, 128, 64, 96, 3, 1, 1),     # a row is exactly one box; Cout with a ragged N tile
     (1, 256, 256, 64, 32, 3, 1, 1),     # StyleGAN2 256^2 layer: rows of two boxes
     (2, 32, 32, 128, 64, 3, 1, 1),
+    (1, 256, 256, 32, 32, 3, 1, 1),     # StyleGAN2 256^2 layer with 32 channels: 64-byte-swizzle K blocks (forward + dgrad; wgrad explicit)
+    (2, 64, 64, 32, 64, 3, 1, 1),
+    (3, 16, 16, 64, 32, 3, 1, 1),       # Cout = 32: the data gradient runs over a 32-channel dy
 ]
 
 
@@ -48,8 +51,10 @@ def test_implicit_conv_matches_torch(B, H, W, Cin, Cout, k, stride, pad):
     finally:
         K.gemm = real_gemm
     torch.cuda.synchronize()
-    assert 1 in used and 2 in used, used                      # forward (and the stride-1 dgrad) + the weight gradient went implicit
-    if stride == 1 and Cout % 64 == 0:                        # dy has Cout channels: the implicit data gradient needs whole 64-channel blocks
+    assert 1 in used, used                                    # the forward went implicit
+    if Cin % 64 == 0:
+        assert 2 in used, used                                # and so did the weight gradient (whole 64-channel blocks only)
+    if stride == 1 and (Cout % 64 == 0 or Cout == 32):        # dy has Cout channels: the implicit data gradient needs 64-channel blocks or exactly 32
         assert used.count(1) == 2, used
     # fp32 reference on the same bf16-rounded operands
     xr = x.float().view(B, H, W, Cin).permute(0, 3, 1, 2).clone().requires_grad_(True)
@@ -58,10 +63,15 @@ def test_implicit_conv_matches_torch(B, H, W, Cin, Cout, k, stride, pad):
     yr.backward(dy.float().view(B, Ho, Wo, Cout).permute(0, 3, 1, 2))
     y_ref = yr.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Cout)
     dx_ref = xr.grad.permute(0, 2, 3, 1).reshape(B * H * W, Cin)
-    for name, got, ref, tol in (("y", y, y_ref, 1e-2), ("dx", xi.grad, dx_ref, 2e-2), ("dw", w.grad, wr.grad, 2e-2)):
+    # dx / dw: the ReLU mask comes from the bf16 output here and from the fp32 output in the reference — where the pre-activation is
+    # within a rounding of 0 one term of the sum flips, which the max norm sees for short sums (288 terms at 32 channels) — so the
+    # gradients are held to a relative L2 bound and a looser max bound
+    for name, got, ref, tol, tol_l2 in (("y", y, y_ref, 1e-2, 3e-3), ("dx", xi.grad, dx_ref, 6e-2, 1e-2), ("dw", w.grad, wr.grad, 2e-2, 1e-2)):
+        ref = ref.detach()
         sc = float(ref.abs().max()) + 1e-12
         err = float((got.float() - ref).abs().max()) / sc
-        assert err < tol, (name, err)
+        l2 = float((got.float() - ref).norm() / (ref.norm() + 1e-12))
+        assert err < tol and l2 < tol_l2, (name, err, l2)
 
 
 def test_implicit_and_explicit_paths_agree():
