@@ -627,6 +627,8 @@ class Conv2dFn(_Fn):
         else:
             cols = x if direct else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0]
             K.gemm(M, Cout, cols.shape[1], K.Op(cols, cols.stride(0)), K.Op(w16, w16.stride(0)), K.Out(out, Cout), **epi)
+        # the 3-channel stem keeps its (small-K) patch matrix for the weight gradient instead of gathering it twice
+        ctx.cols = cols if (not implicit and not direct and _need(ctx) and _needs(weight) and Cin < 8) else None
         ctx.geom = (B, H, W, stride, pad, Ho, Wo, direct)
         ctx.weight, ctx.act, ctx.scale = weight, act, scale
         ctx.shift_param = shift if isinstance(shift, torch.nn.Parameter) else None
@@ -677,7 +679,7 @@ class Conv2dFn(_Fn):
             sk = E.wgrad_split_k(Cout, Kreal, M)
             implicit = (not direct and IMPLICIT_CONV and Cin % 64 == 0 and x.is_contiguous() and K.conv_box_ok(Ho, Wo, stride, 64))
             cv = _conv_geom(x, 2, B, H, W, Cin, Ho, Wo, KH, KW, stride, pad) if implicit else None
-            cols = x if (direct or implicit) else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0]
+            cols = x if (direct or implicit) else (ctx.cols if ctx.cols is not None else K.im2col(x, B, H, W, Cin, KH, KW, stride, pad)[0])
             if KH == 1 and KW == 1:
                 g2 = g.view(Cout, Cin)
                 K.gemm(Cout, Cin, M, K.Op(dconv, Cout, mn=True), K.Op(cols, cols.stride(0), mn=True), K.Out(g2, Cin),
