@@ -47,7 +47,8 @@ def bench_loop(args, dev, B, world, rank):
     net = lambda kw, cls: dict({k: v for k, v in kw.items() if k not in common}, class_name="layoutdetr_b200.training.networks_detr." + cls)
     ds = dict(class_name="layoutdetr_b200.training.synthetic_dataset.SyntheticLayoutDataset", num_items=4096, n_valid=8, seed=rank)
     marks = {}
-    W, K = max(3, args.warmup), max(20, args.steps)        # wall-clock window: at least 20 iterations (10 are within +-2 % run to run)
+    W, K = max(5, args.warmup), max(40, args.steps)        # wall-clock window of at least 40 iterations: the first iterations after the capture
+    # carry loader start-up and pinned-pool growth (measured: 179 samples/s over 20 iterations, 184 over 60, bare replay 187-188)
 
     def cb(i):
         if i == W or i == W + K:
