@@ -182,7 +182,7 @@ def run_eval(args):
     torch.manual_seed(0)
     G = nd.Generator(**G_KWARGS).to(dev).eval().requires_grad_(False)
     net = LayoutNet(13).to(dev).eval().requires_grad_(False)
-    B, nb = args.eval_batch, max(1, args.steps)
+    B, nb = args.eval_batch, max(16, args.steps)       # >= 16 batches: the sweep ends with ONE host-side FID (256 x 256 sqrtm), which a 4-batch window over-weights
     host = [make_inputs(B, n_valid=8, seed=50 + 1000 * rank + i) for i in range(nb)]      # every rank sweeps its own shard of the layouts
     for hb in host:
         for k, v in hb.items():
