@@ -379,3 +379,30 @@ def test_bucketed_gradient_exchange_gloo_world2():
     assert results == [True, True, True], results
     assert early == 2 * nb, (early, nb)              # both armed passes sent every bucket from inside the backward pass
     assert raised
+
+
+def test_conv_box_rule_and_split_k_model():
+    """Host-side rules of the convolution / weight-gradient paths: a box of output pixels must be whole rows / whole images
+    (mirrors make_conv_map in csrc/gemm_sm100.cu), and the split-K factor stays within its bounds and follows the measured optima of
+    profiles/r2_splitk_probe.txt."""
+    from layoutdetr_b200 import engine as E, kernels as K
+    ok = K.conv_box_ok
+    assert ok(64, 64, 1, 128) and ok(32, 32, 2, 128) and ok(16, 16, 1, 128) and ok(8, 8, 1, 128)       # ResNet-50 stages at 256^2
+    assert ok(256, 256, 1, 128) and ok(128, 128, 1, 64) and ok(4, 4, 1, 64)
+    assert not ok(12, 12, 1, 128) and not ok(24, 24, 1, 128) and not ok(7, 7, 1, 64)
+    assert not ok(64, 192, 1, 128)                              # a row of 192 pixels is not a whole number of 128-pixel boxes
+    assert not ok(8, 128, 4, 128)                               # box of 128 pixels x stride 4 exceeds the 256-element TMA box limit
+    old = E._SM_COUNT
+    E._SM_COUNT = 148
+    try:
+        for shape in [(256, 64, 65536), (64, 576, 65536), (512, 128, 16384), (256, 2304, 4096), (512, 4608, 1024), (768, 768, 32768),
+                      (30524, 768, 32768), (256, 256, 160), (32, 288, 1048576), (8, 8, 64), (3, 32, 1048576)]:
+            sk = E.wgrad_split_k(*shape)
+            kb = (shape[2] + 63) // 64
+            assert 1 <= sk <= max(1, kb // 2), (shape, sk)
+        assert E.wgrad_split_k(512, 4608, 1024) == 1            # many tiles, short reduction: never split (measured 15 vs 34 us)
+        assert E.wgrad_split_k(30524, 768, 32768) == 1          # the LM-head weight gradient fills the chip by itself
+        assert 32 <= E.wgrad_split_k(256, 64, 65536) <= 64      # measured optimum 32-64 (20 us; the round-1 rule chose 148: 40 us)
+        assert 4 <= E.wgrad_split_k(768, 768, 32768) <= 8
+    finally:
+        E._SM_COUNT = old
